@@ -91,6 +91,7 @@ typedef struct mpcb_sim_out {
   int8_t *status;        /* [T1-1][B]  OSQP status_val per solve */
   int16_t *iters;        /* [T1-1][B]  ADMM iterations per solve */
   double *u_raw;         /* [2][T1-1][B] selected control before the norm clip (:314) */
+  int32_t *ukf_clamped;  /* [B]  1 if a UKF Cholesky pivot was <= 0 and clamped (the reference raises LinAlgError there) */
 } mpcb_sim_out;
 
 /* Run counters filled by the simulate / qp_solve calls (for bench.py's gpu_launches etc.). */
@@ -151,11 +152,14 @@ int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub_total, int
                              const double *x0, const double *noise, int32_t n_refresh, int32_t noise_hold_sub,
                              const mpcb_sim_out *out, int io_on_device);
 
-/* Reduce final statistics over the batch on the device (test/disturbRejComp.py:89-100,
- * test/saved_runs/success_rates_test.py:66-75): stats[0]=sum final_dist, [1]=sum final_dist^2,
- * [2]=#success, [3]=#lanes, [4]=sum i_term, [5]=total qp solves, [6]=total admm iterations, [7]=flip lanes.
- * The 8 doubles are what ranks all-reduce over NCCL. */
-int mpcb_stats(mpcb_handle *h, int64_t B, double *stats8, int io_on_device);
+/* Final statistics of the last simulation, reduced over the batch on the device
+ * (test/disturbRejComp.py:89-100, test/saved_runs/success_rates_test.py:66-75):
+ * stats[0]=sum final_dist, [1]=sum final_dist^2, [2]=#success, [3]=#lanes, [4]=sum i_term,
+ * [5]=qp solves, [6]=admm iterations, [7]=flip lanes, [8]=lanes with a clamped UKF Cholesky pivot,
+ * [9]=lanes that terminated before the last step.  These MPCB_NSTATS doubles are what ranks
+ * all-reduce (sum) over NCCL. */
+#define MPCB_NSTATS 10
+int mpcb_stats(mpcb_handle *h, int64_t B, double *stats, int io_on_device);
 
 #ifdef __cplusplus
 }

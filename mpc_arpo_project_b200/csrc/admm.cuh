@@ -29,8 +29,8 @@ __device__ __forceinline__ void ell_apply(const double *__restrict__ vals, const
   }
 }
 
-template <int NXS, int MZS, bool VSMEM>
-__global__ void __launch_bounds__(512) admm_block_kernel(const __grid_constant__ AdmmArgs a) {
+template <int NXS, int MZS, bool VSMEM, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) admm_block_kernel(const __grid_constant__ AdmmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -66,10 +66,11 @@ struct LaneSim {            // SoA [field][B] per-lane simulation state
   int *succ;                // [B]
   int *nsolve;              // [B]
   int *variant;             // [B]
+  int *ukf_clamp;           // [B] set when a UKF Cholesky pivot was clamped to zero
 };
 
 struct SimOutDev {
-  int32_t *i_term; int32_t *is_success; double *final_dist;
+  int32_t *i_term; int32_t *is_success; int32_t *ukf_clamped; double *final_dist;
   double *x_true, *x_est, *ctrl; uint8_t *ctrlr_seq; int8_t *status; int16_t *iters; double *u_raw;
   int T1;
 };

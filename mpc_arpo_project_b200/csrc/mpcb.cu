@@ -1,0 +1,819 @@
+// libmpcb.so -- C ABI (include/mpcb.h) over the sm_100a kernels in admm.cuh / sim.cuh.
+// Host side only: table upload, per-batch state, the lockstep round loop, I/O staging.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcb.h"
+#include "admm.cuh"
+#include "common.cuh"
+#include "sim.cuh"
+
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      char b_[512];                                                                                      \
+      snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return fail(e_ == cudaErrorMemoryAllocation ? MPCB_ERR_NOMEM : MPCB_ERR_CUDA, b_);                 \
+    }                                                                                                    \
+  } while (0)
+
+typedef void (*admm_fn)(const AdmmArgs);
+
+struct KernelChoice {
+  admm_fn fn = nullptr;
+  int max_warps = 0;
+};
+
+template <int NXS, int MZS, bool VS, int WARPS>
+static KernelChoice pick() {
+  KernelChoice k;
+  k.fn = admm_block_kernel<NXS, MZS, VS, WARPS>;
+  k.max_warps = WARPS;
+  return k;
+}
+
+// Instantiations cover the reference's Nc = Nb = 5 problem family at the horizons the reference
+// scripts and BASELINE.json use: Nx = 10, 20, 30, 40 (n = 4Nx+41, m = 9Nx+46).
+static KernelChoice choose_kernel(int nxs, int mzs, bool vs) {
+#define TRY(NX_, MZ_, W_)                                                      \
+  if (nxs == NX_ && mzs == MZ_) return vs ? pick<NX_, MZ_, true, W_>() : pick<NX_, MZ_, false, W_>();
+  TRY(3, 5, 16) TRY(4, 8, 8) TRY(6, 10, 8) TRY(7, 13, 8)
+#undef TRY
+  return KernelChoice();
+}
+
+struct HostProblem {
+  mpcb_problem p;
+  std::vector<double> P_s, q_s, A_s, l_s, u_s, D, E, V, lam;
+  std::vector<int32_t> ctype;
+};
+
+struct mpcb_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  HostProblem hp;
+  SimConst sc;
+  // constant tables
+  BlobHdr hdr;
+  unsigned char *d_blob[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_V[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool vsmem = false;
+  KernelChoice kern;
+  int warps = 8;
+  size_t smem_bytes = 0;
+  double qn_unscaled = 0, qn_scaled = 0;
+  int num_sms = 148;
+  // batch state
+  int64_t B = 0;
+  double *xs = nullptr, *zs = nullptr, *ys = nullptr, *rho = nullptr, *par = nullptr, *u0 = nullptr;
+  int *iter = nullptr, *status = nullptr, *flip = nullptr;
+  uint8_t *lane_state = nullptr;
+  int *cnt = nullptr;    // [2][4]
+  int *list = nullptr;   // [2][4][B]
+  LaneSim ls;
+  double *lane_f64 = nullptr;   // backing store of LaneSim doubles
+  int *lane_i32 = nullptr;      // backing store of LaneSim ints
+  unsigned long long *d_tot = nullptr;   // [0] admm iterations, [1] qp solves
+  double *d_stats = nullptr;             // [MPCB_NSTATS]
+  int *h_cnt = nullptr;                  // pinned [4]
+  bool sim_done = false;
+  int64_t last_sim_iterations = 0;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  mpcb_counters ctr;
+};
+
+// ------------------------------------------------------------------------------------------
+// grouped ELL: rows in groups of 32 (row = lane + 32*s); a group stores width*32 entries [e][lane].
+struct Ell {
+  std::vector<double> vals;
+  std::vector<uint16_t> cols;
+  std::vector<int2> grp;
+};
+
+static Ell build_ell(const double *M, int rows, int cols, bool transpose, int ngroups) {
+  // logical matrix L(r, c) = transpose ? M[c*rows_in + r] : M[r*cols + c]; `rows`/`cols` are L's dims
+  Ell e;
+  auto at = [&](int r, int c) { return transpose ? M[(size_t)c * rows + r] : M[(size_t)r * cols + c]; };
+  int off = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    int width = 0;
+    for (int ln = 0; ln < 32; ++ln) {
+      const int r = g * 32 + ln;
+      if (r >= rows) continue;
+      int nz = 0;
+      for (int c = 0; c < cols; ++c) nz += (at(r, c) != 0.0);
+      width = std::max(width, nz);
+    }
+    e.grp.push_back(make_int2(off, width));
+    e.vals.resize(off + width * 32, 0.0);
+    e.cols.resize(off + width * 32, 0);
+    for (int ln = 0; ln < 32; ++ln) {
+      const int r = g * 32 + ln;
+      if (r >= rows) continue;
+      int k = 0;
+      for (int c = 0; c < cols; ++c) {
+        const double v = at(r, c);
+        if (v != 0.0) {
+          e.vals[off + k * 32 + ln] = v;
+          e.cols[off + k * 32 + ln] = (uint16_t)c;
+          ++k;
+        }
+      }
+    }
+    off += width * 32;
+  }
+  return e;
+}
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+static void variant_matrix(const HostProblem &hp, int v, std::vector<double> &A) {
+  const mpcb_problem &p = hp.p;
+  A = hp.A_s;
+  const int nX = 4 * (p.Nx + 1);
+  for (int k = 0; k <= p.Nx; ++k) {
+    const int r = nX + 5 * k + 3;
+    if (v & 1) A[(size_t)r * p.n + 4 * k + 2] *= -1.0;
+    if (v & 2) A[(size_t)r * p.n + 4 * k + 3] *= -1.0;
+  }
+}
+
+static int build_tables(mpcb_handle *h) {
+  const HostProblem &hp = h->hp;
+  const mpcb_problem &p = hp.p;
+  const int n = p.n, m = p.m;
+  const int nxs = (n + 31) / 32, mzs = (m + 31) / 32;
+  std::vector<std::vector<unsigned char>> blobs(4);
+  BlobHdr hdr;
+  memset(&hdr, 0, sizeof hdr);
+  // Does V fit in shared memory next to the rest?  Decide after the first variant's layout is known.
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int v = 0; v < 4; ++v) {
+      std::vector<double> A;
+      variant_matrix(hp, v, A);
+      Ell eA = build_ell(A.data(), m, n, false, mzs);
+      Ell eAT = build_ell(A.data(), n, m, true, nxs);
+      Ell eP = build_ell(hp.P_s.data(), n, n, false, nxs);
+      int off = 0;
+      auto take = [&](int bytes) {
+        const int o = off;
+        off = align16(off + bytes);
+        return o;
+      };
+      BlobHdr hv;
+      memset(&hv, 0, sizeof hv);
+      hv.off_lam = take(8 * n);
+      hv.off_q = take(8 * n);
+      hv.off_D = take(8 * n);
+      hv.off_Dinv = take(8 * n);
+      hv.off_E = take(8 * m);
+      hv.off_Einv = take(8 * m);
+      hv.off_lt = take(8 * m);
+      hv.off_ut = take(8 * m);
+      hv.off_Av = take(8 * (int)eA.vals.size());
+      hv.off_ATv = take(8 * (int)eAT.vals.size());
+      hv.off_Pv = take(8 * (int)eP.vals.size());
+      hv.off_Ac = take(2 * (int)eA.cols.size());
+      hv.off_ATc = take(2 * (int)eAT.cols.size());
+      hv.off_Pc = take(2 * (int)eP.cols.size());
+      hv.off_Ag = take(8 * (int)eA.grp.size());
+      hv.off_ATg = take(8 * (int)eAT.grp.size());
+      hv.off_Pg = take(8 * (int)eP.grp.size());
+      hv.off_flags = take(m);
+      hv.off_V = (pass == 1 && h->vsmem) ? take(8 * n * n) : -1;
+      hv.total = off;
+      if (v == 0) hdr = hv;
+      else if (memcmp(&hdr, &hv, sizeof hv) != 0)
+        return fail(MPCB_ERR_INVALID, "sign variants do not share one sparsity layout");
+      if (pass == 0) continue;
+      std::vector<unsigned char> &b = blobs[v];
+      b.assign(hv.total, 0);
+      auto putd = [&](int o, const double *src, size_t cnt) { memcpy(b.data() + o, src, cnt * 8); };
+      std::vector<double> Dinv(n), Einv(m);
+      for (int j = 0; j < n; ++j) Dinv[j] = 1.0 / hp.D[j];
+      for (int i = 0; i < m; ++i) Einv[i] = 1.0 / hp.E[i];
+      putd(hv.off_lam, hp.lam.data() + (size_t)v * n, n);
+      putd(hv.off_q, hp.q_s.data(), n);
+      putd(hv.off_D, hp.D.data(), n);
+      putd(hv.off_Dinv, Dinv.data(), n);
+      putd(hv.off_E, hp.E.data(), m);
+      putd(hv.off_Einv, Einv.data(), m);
+      putd(hv.off_lt, hp.l_s.data(), m);
+      putd(hv.off_ut, hp.u_s.data(), m);
+      putd(hv.off_Av, eA.vals.data(), eA.vals.size());
+      putd(hv.off_ATv, eAT.vals.data(), eAT.vals.size());
+      putd(hv.off_Pv, eP.vals.data(), eP.vals.size());
+      memcpy(b.data() + hv.off_Ac, eA.cols.data(), eA.cols.size() * 2);
+      memcpy(b.data() + hv.off_ATc, eAT.cols.data(), eAT.cols.size() * 2);
+      memcpy(b.data() + hv.off_Pc, eP.cols.data(), eP.cols.size() * 2);
+      memcpy(b.data() + hv.off_Ag, eA.grp.data(), eA.grp.size() * 8);
+      memcpy(b.data() + hv.off_ATg, eAT.grp.data(), eAT.grp.size() * 8);
+      memcpy(b.data() + hv.off_Pg, eP.grp.data(), eP.grp.size() * 8);
+      for (int i = 0; i < m; ++i) {
+        uint8_t f = 0;
+        if (hp.l_s[i] < -1e30 * 1e-4) f |= 1;
+        if (hp.u_s[i] > 1e30 * 1e-4) f |= 2;
+        if (hp.ctype[i] == 1) f |= 4;
+        if (hp.ctype[i] == -1) f |= 8;
+        b[hv.off_flags + i] = f;
+      }
+      if (hv.off_V >= 0) putd(hv.off_V, hp.V.data() + (size_t)v * n * n, (size_t)n * n);
+    }
+    if (pass == 0) {
+      // per-warp scratch (m + 2n doubles) + barrier; aim for >= 8 warps with V resident
+      const int fixed = hdr.total + 16;
+      const int withV = fixed + 8 * n * n;
+      h->vsmem = (withV + 8 * 8 * (m + 2 * n)) <= 220 * 1024;
+    }
+  }
+  h->hdr = hdr;
+  h->kern = choose_kernel(nxs, mzs, h->vsmem);
+  if (!h->kern.fn) {
+    char b[160];
+    snprintf(b, sizeof b, "no ADMM kernel instantiation for n=%d m=%d (Nc = 5 with Nx in {10, 20, 30, 40} supported)", n, m);
+    return fail(MPCB_ERR_INVALID, b);
+  }
+  // warps per CTA: as many as fit in shared memory, capped by the instantiation's launch bound
+  const int per_warp = 8 * (m + 2 * n);
+  int w = (int)((220 * 1024 - (hdr.total + 16)) / per_warp);
+  w = std::min(w, h->kern.max_warps);
+  if (w < 1) return fail(MPCB_ERR_INVALID, "problem too large for shared memory staging");
+  h->warps = w;
+  for (int v = 0; v < 4; ++v) {
+    CK(cudaMalloc(&h->d_blob[v], hdr.total));
+    CK(cudaMemcpy(h->d_blob[v], blobs[v].data(), hdr.total, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_V[v], (size_t)8 * n * n));
+    CK(cudaMemcpy(h->d_V[v], hp.V.data() + (size_t)v * n * n, (size_t)8 * n * n, cudaMemcpyHostToDevice));
+  }
+  double qu = 0, qs = 0;
+  for (int j = 0; j < n; ++j) {
+    qu = std::max(qu, fabs(hp.q_s[j] / hp.D[j]));
+    qs = std::max(qs, fabs(hp.q_s[j]));
+  }
+  h->qn_unscaled = qu;
+  h->qn_scaled = qs;
+  return MPCB_OK;
+}
+
+static void set_warps(mpcb_handle *h, int w) {
+  h->warps = w;
+  h->smem_bytes = (size_t)h->hdr.total + 16 + (size_t)w * 8 * (h->hp.p.m + 2 * h->hp.p.n);
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
+extern "C" const char *mpcb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out) {
+  if (!pr || !out) return fail(MPCB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int n = pr->n, m = pr->m;
+  if (pr->Nx < 1 || pr->Nc < 1 || pr->Nc > pr->Nx || pr->Nb < 0 || pr->Nb > pr->Nx)
+    return fail(MPCB_ERR_INVALID, "bad horizons");
+  if (n != 4 * (pr->Nx + 1) + 7 * pr->Nc + 2 || m != 9 * (pr->Nx + 1) + 7 * pr->Nc + 2)
+    return fail(MPCB_ERR_INVALID, "n/m do not match the horizons");
+  if (!pr->P_s || !pr->q_s || !pr->A_s || !pr->l_s || !pr->u_s || !pr->D || !pr->E || !pr->ctype || !pr->V || !pr->lam)
+    return fail(MPCB_ERR_INVALID, "null table pointer");
+  if (pr->check_termination < 1 || pr->max_iter % pr->check_termination != 0 ||
+      (pr->adaptive_rho && (pr->adaptive_rho_interval < 1 || pr->adaptive_rho_interval % pr->check_termination != 0)))
+    return fail(MPCB_ERR_INVALID, "max_iter and adaptive_rho_interval must be multiples of check_termination");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(MPCB_ERR_INVALID, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  mpcb_handle *h = new mpcb_handle();
+  h->device = device;
+  memset(&h->ctr, 0, sizeof h->ctr);
+  memset(&h->ls, 0, sizeof h->ls);
+  HostProblem &hp = h->hp;
+  hp.p = *pr;
+  hp.P_s.assign(pr->P_s, pr->P_s + (size_t)n * n);
+  hp.q_s.assign(pr->q_s, pr->q_s + n);
+  hp.A_s.assign(pr->A_s, pr->A_s + (size_t)m * n);
+  hp.l_s.assign(pr->l_s, pr->l_s + m);
+  hp.u_s.assign(pr->u_s, pr->u_s + m);
+  hp.D.assign(pr->D, pr->D + n);
+  hp.E.assign(pr->E, pr->E + m);
+  hp.V.assign(pr->V, pr->V + (size_t)4 * n * n);
+  hp.lam.assign(pr->lam, pr->lam + (size_t)4 * n);
+  hp.ctype.assign(pr->ctype, pr->ctype + m);
+  hp.p.P_s = hp.p.q_s = hp.p.A_s = hp.p.l_s = hp.p.u_s = hp.p.D = hp.p.E = hp.p.V = hp.p.lam = nullptr;
+  hp.p.ctype = nullptr;
+  SimConst &sc = h->sc;
+  memcpy(sc.Ad, pr->Ad, sizeof sc.Ad);
+  memcpy(sc.Bd, pr->Bd, sizeof sc.Bd);
+  memcpy(sc.Ao, pr->Ao, sizeof sc.Ao);
+  memcpy(sc.Bou, pr->Bou, sizeof sc.Bou);
+  memcpy(sc.Qw, pr->Qw, sizeof sc.Qw);
+  memcpy(sc.Kpf, pr->Kpf, sizeof sc.Kpf);
+  memcpy(sc.Kif, pr->Kif, sizeof sc.Kif);
+  memcpy(sc.xr, pr->xr, sizeof sc.xr);
+  sc.umax0 = pr->umax0; sc.r_p = pr->r_p; sc.r_tol = pr->r_tol; sc.suc_dist = pr->suc_dist;
+  sc.suc_ang_deg = pr->suc_ang_deg; sc.mean_mtn = pr->mean_mtn;
+  sc.in_track = pr->in_track; sc.delta_v = pr->delta_v; sc.is_reject = pr->is_reject; sc.has_noise = pr->has_noise;
+  sc.noise_length = std::max(1, pr->noise_length);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  int rc = build_tables(h);
+  if (rc != MPCB_OK) {
+    mpcb_destroy(h);
+    return rc;
+  }
+  set_warps(h, h->warps);
+  CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&h->d_tot, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_stats, MPCB_NSTATS * sizeof(double)));
+  CK(cudaMallocHost(&h->h_cnt, 8 * sizeof(int)));
+  CK(cudaEventCreate(&h->ev_t0));
+  CK(cudaEventCreate(&h->ev_t1));
+  *out = h;
+  return MPCB_OK;
+}
+
+static void free_batch(mpcb_handle *h) {
+  cudaFree(h->xs); cudaFree(h->zs); cudaFree(h->ys); cudaFree(h->rho); cudaFree(h->par); cudaFree(h->u0);
+  cudaFree(h->iter); cudaFree(h->status); cudaFree(h->flip); cudaFree(h->lane_state); cudaFree(h->cnt);
+  cudaFree(h->list); cudaFree(h->lane_f64); cudaFree(h->lane_i32);
+  h->xs = h->zs = h->ys = h->rho = h->par = h->u0 = h->lane_f64 = nullptr;
+  h->iter = h->status = h->flip = h->cnt = h->list = h->lane_i32 = nullptr;
+  h->lane_state = nullptr;
+  h->B = 0;
+}
+
+extern "C" int mpcb_destroy(mpcb_handle *h) {
+  if (!h) return MPCB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_batch(h);
+  for (int v = 0; v < 4; ++v) {
+    cudaFree(h->d_blob[v]);
+    cudaFree(h->d_V[v]);
+  }
+  cudaFree(h->d_tot);
+  cudaFree(h->d_stats);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MPCB_OK;
+}
+
+static int reset_solver_state(mpcb_handle *h) {
+  const int64_t B = h->B;
+  const int n = h->hp.p.n, m = h->hp.p.m;
+  CK(cudaMemsetAsync(h->xs, 0, (size_t)B * n * 8, h->stream));
+  CK(cudaMemsetAsync(h->zs, 0, (size_t)B * m * 8, h->stream));
+  CK(cudaMemsetAsync(h->ys, 0, (size_t)B * m * 8, h->stream));
+  CK(cudaMemsetAsync(h->flip, 0, (size_t)B * 4, h->stream));
+  CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_tot, 0, 2 * sizeof(unsigned long long), h->stream));
+  std::vector<double> r((size_t)B, std::min(std::max(h->hp.p.rho0, MPCB_RHO_MIN), MPCB_RHO_MAX));
+  CK(cudaMemcpyAsync(h->rho, r.data(), (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->sim_done = false;
+  return MPCB_OK;
+}
+
+extern "C" int mpcb_batch_alloc(mpcb_handle *h, int64_t B) {
+  if (!h || B < 1 || B > (int64_t)1 << 30) return fail(MPCB_ERR_INVALID, "bad batch size");
+  CK(cudaSetDevice(h->device));
+  if (h->B != B) {
+    free_batch(h);
+    const int n = h->hp.p.n, m = h->hp.p.m;
+    CK(cudaMalloc(&h->xs, (size_t)B * n * 8));
+    CK(cudaMalloc(&h->zs, (size_t)B * m * 8));
+    CK(cudaMalloc(&h->ys, (size_t)B * m * 8));
+    CK(cudaMalloc(&h->rho, (size_t)B * 8));
+    CK(cudaMalloc(&h->par, (size_t)B * 7 * 8));
+    CK(cudaMalloc(&h->u0, (size_t)B * 2 * 8));
+    CK(cudaMalloc(&h->iter, (size_t)B * 4));
+    CK(cudaMalloc(&h->status, (size_t)B * 4));
+    CK(cudaMalloc(&h->flip, (size_t)B * 4));
+    CK(cudaMalloc(&h->lane_state, (size_t)B));
+    CK(cudaMalloc(&h->cnt, 8 * sizeof(int)));
+    CK(cudaMalloc(&h->list, (size_t)8 * B * sizeof(int)));
+    // LaneSim: doubles 4+6+36+4+2+2+1+2+4 = 61 per lane, ints 7 per lane
+    CK(cudaMalloc(&h->lane_f64, (size_t)B * 61 * 8));
+    CK(cudaMalloc(&h->lane_i32, (size_t)B * 7 * 4));
+    double *d = h->lane_f64;
+    LaneSim &ls = h->ls;
+    ls.xtrue = d; d += 4 * B;
+    ls.ux = d; d += 6 * B;
+    ls.uP = d; d += 36 * B;
+    ls.xstore = d; d += 4 * B;
+    ls.uprev = d; d += 2 * B;
+    ls.unext = d; d += 2 * B;
+    ls.xintf = d; d += B;
+    ls.noise = d; d += 2 * B;
+    ls.xfin = d; d += 4 * B;
+    int *q = h->lane_i32;
+    ls.step = q; q += B;
+    ls.sub = q; q += B;
+    ls.iterm = q; q += B;
+    ls.succ = q; q += B;
+    ls.nsolve = q; q += B;
+    ls.variant = q; q += B;
+    ls.ukf_clamp = q; q += B;
+    h->B = B;
+  }
+  CK(cudaMemsetAsync(h->lane_f64, 0, (size_t)B * 61 * 8, h->stream));
+  CK(cudaMemsetAsync(h->lane_i32, 0, (size_t)B * 7 * 4, h->stream));
+  return reset_solver_state(h);
+}
+
+extern "C" int mpcb_set_timing(mpcb_handle *h, int enable) {
+  if (!h) return fail(MPCB_ERR_INVALID, "null handle");
+  h->timing = enable != 0;
+  return MPCB_OK;
+}
+
+extern "C" int mpcb_get_counters(mpcb_handle *h, mpcb_counters *out) {
+  if (!h || !out) return fail(MPCB_ERR_INVALID, "null argument");
+  *out = h->ctr;
+  return MPCB_OK;
+}
+
+extern "C" void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+static void fill_args(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int mode) {
+  const mpcb_problem &p = h->hp.p;
+  memset(&aa, 0, sizeof aa);
+  aa.hdr = h->hdr;
+  for (int v = 0; v < 4; ++v) {
+    aa.blob[v] = h->d_blob[v];
+    aa.Vg[v] = h->d_V[v];
+  }
+  aa.n = p.n; aa.m = p.m; aa.nX = 4 * (p.Nx + 1); aa.Nx = p.Nx; aa.Nb = p.Nb; aa.uoff = 4 * (p.Nx + 1);
+  aa.B = (int)h->B;
+  aa.sigma = p.sigma; aa.alpha = p.alpha; aa.eps_abs = p.eps_abs; aa.eps_rel = p.eps_rel; aa.eps_pinf = p.eps_prim_inf;
+  aa.adapt_tol = p.adaptive_rho_tolerance; aa.cinv = 1.0 / p.c;
+  aa.qn_unscaled = h->qn_unscaled; aa.qn_scaled = h->qn_scaled;
+  aa.check_every = p.check_termination; aa.adaptive = p.adaptive_rho; aa.adapt_interval = std::max(1, p.adaptive_rho_interval);
+  aa.max_iter = p.max_iter;
+  aa.xs = h->xs; aa.zs = h->zs; aa.ys = h->ys; aa.rho = h->rho; aa.iter = h->iter; aa.status = h->status;
+  aa.par = h->par; aa.u0 = h->u0; aa.lane_state = h->lane_state; aa.flip = h->flip; aa.iter_total = h->d_tot;
+  memset(&pa, 0, sizeof pa);
+  pa.sc = h->sc;
+  pa.ls = h->ls;
+  pa.mode = mode;
+  pa.B = (int)h->B;
+  pa.par = h->par; pa.u0 = h->u0; pa.rho = h->rho; pa.iter = h->iter; pa.status = h->status;
+  pa.lane_state = h->lane_state;
+  pa.solves_total = h->d_tot + 1;
+}
+
+// The lockstep round loop: every round runs one check_termination block of ADMM for all
+// still-solving lanes, then the per-lane epilogue for the lanes whose solve ended.
+static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf) {
+  const int64_t B = h->B;
+  const int W = h->warps;
+  const int pgrid = (int)((B + 127) / 128);
+  int cur = first_buf;
+  size_t ev_used = 0;
+  while (true) {
+    CK(cudaMemcpyAsync(h->h_cnt, h->cnt + 4 * cur, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int grid = 0;
+    long live = 0;
+    for (int v = 0; v < 4; ++v) {
+      grid += (h->h_cnt[v] + W - 1) / W;
+      live += h->h_cnt[v];
+    }
+    if (live == 0) break;
+    aa.cnt = h->cnt + 4 * cur;
+    aa.list = h->list + (size_t)4 * B * cur;
+    pa.cnt_cur = h->cnt + 4 * cur;
+    pa.cnt_next = h->cnt + 4 * (1 - cur);
+    pa.list_next = h->list + (size_t)4 * B * (1 - cur);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+      while (h->ev_pool.size() < ev_used + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev_pool.push_back(e);
+      }
+      e0 = h->ev_pool[ev_used++];
+      e1 = h->ev_pool[ev_used++];
+      CK(cudaEventRecord(e0, h->stream));
+    }
+    h->kern.fn<<<grid, 32 * W, h->smem_bytes, h->stream>>>(aa);
+    if (h->timing) CK(cudaEventRecord(e1, h->stream));
+    post_kernel<<<pgrid, 128, 0, h->stream>>>(pa);
+    CK(cudaGetLastError());
+    h->ctr.kernel_launches += 2;
+    h->ctr.admm_launches += 1;
+    h->ctr.rounds += 1;
+    cur = 1 - cur;
+  }
+  if (h->timing) {
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+      h->ctr.admm_ms += ms;
+    }
+  }
+  return MPCB_OK;
+}
+
+static int pull_totals(mpcb_handle *h) {
+  unsigned long long t[2];
+  CK(cudaMemcpyAsync(t, h->d_tot, sizeof t, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->ctr.admm_iterations += (int64_t)t[0];
+  CK(cudaMemsetAsync(h->d_tot, 0, sizeof t, h->stream));
+  return MPCB_OK;
+}
+
+// Staging of host <-> device batch arrays
+struct Stage {
+  std::vector<void *> owned;
+  ~Stage() {
+    for (void *p : owned) cudaFree(p);
+  }
+  template <typename T>
+  int in(const T *src, size_t count, int on_device, cudaStream_t s, const T **out) {
+    if (!src) { *out = nullptr; return MPCB_OK; }
+    if (on_device) { *out = src; return MPCB_OK; }
+    void *d = nullptr;
+    CK(cudaMalloc(&d, count * sizeof(T)));
+    owned.push_back(d);
+    CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    *out = (const T *)d;
+    return MPCB_OK;
+  }
+  template <typename T>
+  int out(T *dst, size_t count, int on_device, T **dev) {
+    if (!dst) { *dev = nullptr; return MPCB_OK; }
+    if (on_device) { *dev = dst; return MPCB_OK; }
+    void *d = nullptr;
+    CK(cudaMalloc(&d, count * sizeof(T)));
+    owned.push_back(d);
+    *dev = (T *)d;
+    return MPCB_OK;
+  }
+  template <typename T>
+  int back(T *dst, const T *dev, size_t count, int on_device, cudaStream_t s) {
+    if (!dst || on_device) return MPCB_OK;
+    CK(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    return MPCB_OK;
+  }
+};
+#define RC(call)                 \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_ != MPCB_OK) return rc_; \
+  } while (0)
+
+__global__ void gather_qp_out_kernel(int B, const int *__restrict__ status, const int *__restrict__ iter,
+                                     int32_t *__restrict__ st_out, int32_t *__restrict__ it_out) {
+  const int ln = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= B) return;
+  if (st_out) st_out[ln] = status[ln];
+  if (it_out) it_out[ln] = iter[ln];
+}
+
+extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, double *u0, int32_t *status, int32_t *iters,
+                             int io_on_device) {
+  if (!h || !xhat) return fail(MPCB_ERR_INVALID, "null argument");
+  if (h->B == 0 || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_batch_alloc(B) must precede mpcb_qp_solve with the same B");
+  CK(cudaSetDevice(h->device));
+  Stage st;
+  const double *d_xhat;
+  double *d_u0;
+  int32_t *d_st, *d_it;
+  RC(st.in(xhat, (size_t)6 * B, io_on_device, h->stream, &d_xhat));
+  RC(st.out(u0, (size_t)2 * B, io_on_device, &d_u0));
+  RC(st.out(status, (size_t)B, io_on_device, &d_st));
+  RC(st.out(iters, (size_t)B, io_on_device, &d_it));
+  AdmmArgs aa;
+  PostArgs pa;
+  fill_args(h, aa, pa, MODE_QP_ONLY);
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
+  pa.cnt_cur = h->cnt + 4;
+  pa.cnt_next = h->cnt;
+  pa.list_next = h->list;
+  const int pgrid = (int)((B + 127) / 128);
+  qp_prepare_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_xhat);
+  h->ctr.kernel_launches += 1;
+  RC(run_rounds(h, aa, pa, 0));
+  if (d_u0) CK(cudaMemcpyAsync(d_u0, h->u0, (size_t)2 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (d_st || d_it) {
+    gather_qp_out_kernel<<<pgrid, 128, 0, h->stream>>>((int)B, h->status, h->iter, d_st, d_it);
+    h->ctr.kernel_launches += 1;
+  }
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  RC(st.back(u0, d_u0, (size_t)2 * B, io_on_device, h->stream));
+  RC(st.back(status, d_st, (size_t)B, io_on_device, h->stream));
+  RC(st.back(iters, d_it, (size_t)B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+  h->ctr.total_ms += ms;
+  h->ctr.qp_solves += B;
+  return pull_totals(h);
+}
+
+extern "C" int mpcb_qp_get_state(mpcb_handle *h, int64_t lane, double *x, double *z, double *y, double *rho) {
+  if (!h || lane < 0 || lane >= h->B) return fail(MPCB_ERR_INVALID, "bad lane");
+  CK(cudaSetDevice(h->device));
+  const int n = h->hp.p.n, m = h->hp.p.m;
+  CK(cudaStreamSynchronize(h->stream));
+  if (x) CK(cudaMemcpy(x, h->xs + (size_t)lane * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (z) CK(cudaMemcpy(z, h->zs + (size_t)lane * m, (size_t)m * 8, cudaMemcpyDeviceToHost));
+  if (y) CK(cudaMemcpy(y, h->ys + (size_t)lane * m, (size_t)m * 8, cudaMemcpyDeviceToHost));
+  if (rho) CK(cudaMemcpy(rho, h->rho + lane, 8, cudaMemcpyDeviceToHost));
+  return MPCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mpcb_ukf_step(mpcb_handle *h, int64_t B, double *x, double *P, const double *u, const double *z,
+                             int io_on_device) {
+  if (!h || !x || !P || !u || !z || B < 1) return fail(MPCB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  Stage st;
+  const double *dxi, *dPi, *du, *dz;
+  RC(st.in((const double *)x, (size_t)6 * B, io_on_device, h->stream, &dxi));
+  RC(st.in((const double *)P, (size_t)36 * B, io_on_device, h->stream, &dPi));
+  RC(st.in(u, (size_t)2 * B, io_on_device, h->stream, &du));
+  RC(st.in(z, (size_t)2 * B, io_on_device, h->stream, &dz));
+  ukf_step_kernel<<<(int)((B + 63) / 64), 64, 0, h->stream>>>(h->sc, (int)B, (double *)dxi, (double *)dPi, du, dz);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  RC(st.back(x, dxi, (size_t)6 * B, io_on_device, h->stream));
+  RC(st.back(P, dPi, (size_t)36 * B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MPCB_OK;
+}
+
+extern "C" int mpcb_plant_lin_step(mpcb_handle *h, int64_t B, double *x, const double *u, const double *w, int io_on_device) {
+  if (!h || !x || !u || B < 1) return fail(MPCB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->device));
+  Stage st;
+  const double *dx, *du, *dw;
+  RC(st.in((const double *)x, (size_t)4 * B, io_on_device, h->stream, &dx));
+  RC(st.in(u, (size_t)2 * B, io_on_device, h->stream, &du));
+  RC(st.in(w, (size_t)2 * B, io_on_device, h->stream, &dw));
+  plant_lin_kernel<<<(int)((B + 127) / 128), 128, 0, h->stream>>>(h->sc, (int)B, (double *)dx, du, dw);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  RC(st.back(x, dx, (size_t)4 * B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MPCB_OK;
+}
+
+extern "C" int mpcb_plant_rk4(mpcb_handle *h, int64_t B, double *x, const double *u, const double *w, int nsub, double dt,
+                              int io_on_device) {
+  if (!h || !x || !u || B < 1 || nsub < 0) return fail(MPCB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  Stage st;
+  const double *dx, *du, *dw;
+  RC(st.in((const double *)x, (size_t)4 * B, io_on_device, h->stream, &dx));
+  RC(st.in(u, (size_t)2 * B, io_on_device, h->stream, &du));
+  RC(st.in(w, (size_t)2 * B, io_on_device, h->stream, &dw));
+  plant_rk4_kernel<<<(int)((B + 127) / 128), 128, 0, h->stream>>>(h->sc, (int)B, (double *)dx, du, dw, nsub, dt);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  RC(st.back(x, dx, (size_t)4 * B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MPCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t n_sub_total, int32_t ratio, double T_cont,
+                    const double *x0, const double *noise, int32_t n_refresh, int32_t noise_hold_sub,
+                    const mpcb_sim_out *out, int io_on_device) {
+  if (!h || !x0) return fail(MPCB_ERR_INVALID, "null argument");
+  if (h->B == 0 || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_batch_alloc(B) must precede a simulation with the same B");
+  if (nsteps < 0) return fail(MPCB_ERR_INVALID, "negative step count");
+  if (h->sc.has_noise && (!noise || n_refresh < 1)) return fail(MPCB_ERR_INVALID, "has_noise problems need a noise tensor");
+  CK(cudaSetDevice(h->device));
+  RC(mpcb_batch_alloc(h, B));   // cold start: x = z = y = 0, rho = rho0 (a fresh osqp.setup, :242-245)
+  static const mpcb_sim_out none = {};
+  const mpcb_sim_out &o = out ? *out : none;
+  const size_t T1 = (size_t)nsteps + 1;
+  Stage st;
+  const double *d_x0, *d_noise;
+  RC(st.in(x0, (size_t)4 * B, io_on_device, h->stream, &d_x0));
+  RC(st.in(noise, noise ? (size_t)n_refresh * 2 * B : 0, io_on_device, h->stream, &d_noise));
+  SimOutDev od;
+  memset(&od, 0, sizeof od);
+  od.T1 = (int)T1;
+  RC(st.out(o.i_term, (size_t)B, io_on_device, &od.i_term));
+  RC(st.out(o.is_success, (size_t)B, io_on_device, &od.is_success));
+  RC(st.out(o.final_dist, (size_t)B, io_on_device, &od.final_dist));
+  RC(st.out(o.x_true, 4 * T1 * B, io_on_device, &od.x_true));
+  RC(st.out(o.x_est, 6 * T1 * B, io_on_device, &od.x_est));
+  RC(st.out(o.ctrl, 2 * T1 * B, io_on_device, &od.ctrl));
+  RC(st.out(o.ctrlr_seq, (T1 - 1) * B, io_on_device, &od.ctrlr_seq));
+  RC(st.out(o.status, (T1 - 1) * B, io_on_device, &od.status));
+  RC(st.out(o.iters, (T1 - 1) * B, io_on_device, &od.iters));
+  RC(st.out(o.u_raw, 2 * (T1 - 1) * B, io_on_device, &od.u_raw));
+  RC(st.out(o.ukf_clamped, (size_t)B, io_on_device, &od.ukf_clamped));
+  // lanes that stop early leave the rest of their telemetry columns undefined in the reference
+  // (np.empty, :258-262); here they read NaN / 0
+  if (od.x_true) CK(cudaMemsetAsync(od.x_true, 0xff, 4 * T1 * B * 8, h->stream));
+  if (od.x_est) CK(cudaMemsetAsync(od.x_est, 0xff, 6 * T1 * B * 8, h->stream));
+  if (od.ctrl) CK(cudaMemsetAsync(od.ctrl, 0xff, 2 * T1 * B * 8, h->stream));
+  if (od.u_raw) CK(cudaMemsetAsync(od.u_raw, 0xff, 2 * (T1 - 1) * B * 8, h->stream));
+  if (od.ctrlr_seq) CK(cudaMemsetAsync(od.ctrlr_seq, 0, (T1 - 1) * B, h->stream));
+  if (od.status) CK(cudaMemsetAsync(od.status, 0, (T1 - 1) * B, h->stream));
+  if (od.iters) CK(cudaMemsetAsync(od.iters, 0, (T1 - 1) * B * 2, h->stream));
+
+  AdmmArgs aa;
+  PostArgs pa;
+  fill_args(h, aa, pa, mode);
+  pa.out = od;
+  pa.nsteps = nsteps;
+  pa.ratio = ratio;
+  pa.n_sub_total = n_sub_total;
+  pa.noise_hold_sub = std::max(1, noise_hold_sub);
+  pa.T_cont = T_cont;
+  pa.noise_in = d_noise;
+  pa.n_refresh = n_refresh;
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  CK(cudaMemsetAsync(h->d_stats, 0, MPCB_NSTATS * sizeof(double), h->stream));
+  pa.cnt_cur = h->cnt + 4;
+  pa.cnt_next = h->cnt;
+  pa.list_next = h->list;
+  const int pgrid = (int)((B + 127) / 128);
+  init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  RC(run_rounds(h, aa, pa, 0));
+  finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  RC(st.back(o.i_term, od.i_term, (size_t)B, io_on_device, h->stream));
+  RC(st.back(o.is_success, od.is_success, (size_t)B, io_on_device, h->stream));
+  RC(st.back(o.final_dist, od.final_dist, (size_t)B, io_on_device, h->stream));
+  RC(st.back(o.x_true, od.x_true, 4 * T1 * B, io_on_device, h->stream));
+  RC(st.back(o.x_est, od.x_est, 6 * T1 * B, io_on_device, h->stream));
+  RC(st.back(o.ctrl, od.ctrl, 2 * T1 * B, io_on_device, h->stream));
+  RC(st.back(o.ctrlr_seq, od.ctrlr_seq, (T1 - 1) * B, io_on_device, h->stream));
+  RC(st.back(o.status, od.status, (T1 - 1) * B, io_on_device, h->stream));
+  RC(st.back(o.iters, od.iters, (T1 - 1) * B, io_on_device, h->stream));
+  RC(st.back(o.u_raw, od.u_raw, 2 * (T1 - 1) * B, io_on_device, h->stream));
+  RC(st.back(o.ukf_clamped, od.ukf_clamped, (size_t)B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+  h->ctr.total_ms += ms;
+  double stats[MPCB_NSTATS];
+  CK(cudaMemcpy(stats, h->d_stats, sizeof stats, cudaMemcpyDeviceToHost));
+  h->ctr.qp_solves += (int64_t)stats[5];
+  h->ctr.flip_lanes += (int64_t)stats[7];
+  h->sim_done = true;
+  const int64_t before = h->ctr.admm_iterations;
+  RC(pull_totals(h));
+  h->last_sim_iterations = h->ctr.admm_iterations - before;
+  return MPCB_OK;
+}
+
+extern "C" int mpcb_simulate_discrete(mpcb_handle *h, int64_t B, int32_t nsteps, const double *x0, const double *noise,
+                                      int32_t n_refresh, const mpcb_sim_out *out, int io_on_device) {
+  return simulate(h, MODE_DISCRETE, B, nsteps, 0, 1, 0.0, x0, noise, n_refresh, 1, out, io_on_device);
+}
+
+extern "C" int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub_total, int32_t ratio, double T_cont,
+                                        const double *x0, const double *noise, int32_t n_refresh, int32_t noise_hold_sub,
+                                        const mpcb_sim_out *out, int io_on_device) {
+  if (ratio < 1 || n_sub_total < 0 || !(T_cont > 0.0)) return fail(MPCB_ERR_INVALID, "bad continuous-time grid");
+  const int32_t n_samples = n_sub_total / ratio;   // nsimD = int(T_final / T) (trajectorySimulateC.py:55-58)
+  return simulate(h, MODE_CONTINUOUS, B, n_samples, n_sub_total, ratio, T_cont, x0, noise, n_refresh, noise_hold_sub, out,
+                  io_on_device);
+}
+
+extern "C" int mpcb_stats(mpcb_handle *h, int64_t B, double *stats_out, int io_on_device) {
+  if (!h || !stats_out) return fail(MPCB_ERR_INVALID, "null argument");
+  if (!h->sim_done || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_stats needs a finished simulation of the same batch");
+  CK(cudaSetDevice(h->device));
+  double s[MPCB_NSTATS];
+  CK(cudaMemcpy(s, h->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+  s[6] = (double)h->last_sim_iterations;
+  if (io_on_device) CK(cudaMemcpy(stats_out, s, sizeof s, cudaMemcpyHostToDevice));
+  else memcpy(stats_out, s, sizeof s);
+  return MPCB_OK;
+}

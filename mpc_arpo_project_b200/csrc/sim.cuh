@@ -54,7 +54,11 @@ __device__ __forceinline__ void rk4_substep(double *x, double u0, double u1, dou
 #define UKF_WC0 (-5.95 / 0.05 + (1.0 - 0.01 + 2.0))
 #define UKF_WI (0.5 / 0.05)
 
-// upper Cholesky U'U = s*P (scipy.linalg.cholesky default), returns false if not PD
+// upper Cholesky U'U = s*P (scipy.linalg.cholesky default, filterpy's `sqrt`).  With R = 0 the
+// posterior covariance is singular in the measured directions and rounding can leave a pivot at
+// -1e-18: the reference then dies with LinAlgError.  The engine continues with the positive
+// SEMI-definite factor instead (pivot <= 0 -> that row of U is zero) and reports the lane
+// (returns false); a pivot of +1e-18 gives the same factor to ~1e-9.
 __device__ __forceinline__ bool chol_upper6(const double *P, double s, double *U) {
   bool ok = true;
   for (int i = 0; i < 6; ++i) {
@@ -63,7 +67,10 @@ __device__ __forceinline__ bool chol_upper6(const double *P, double s, double *U
   for (int i = 0; i < 6; ++i) {
     double d = s * P[i * 6 + i];
     for (int k = 0; k < i; ++k) d -= U[k * 6 + i] * U[k * 6 + i];
-    if (!(d > 0.0)) ok = false;
+    if (!(d > 0.0)) {
+      ok = false;
+      continue;                               // row i stays zero
+    }
     const double r = sqrt(d);
     U[i * 6 + i] = r;
     for (int j = i + 1; j < 6; ++j) {
@@ -75,21 +82,23 @@ __device__ __forceinline__ bool chol_upper6(const double *P, double s, double *U
   return ok;
 }
 
-__device__ __forceinline__ void sigma_points(const double *x, const double *P, double *sig /*[13][6]*/) {
+__device__ __forceinline__ bool sigma_points(const double *x, const double *P, double *sig /*[13][6]*/) {
   double U[36];
-  chol_upper6(P, UKF_NPL, U);
+  const bool ok = chol_upper6(P, UKF_NPL, U);
   for (int j = 0; j < 6; ++j) sig[j] = x[j];
   for (int k = 0; k < 6; ++k)
     for (int j = 0; j < 6; ++j) {
       sig[(k + 1) * 6 + j] = x[j] + U[k * 6 + j];
       sig[(k + 7) * 6 + j] = x[j] - U[k * 6 + j];
     }
+  return ok;
 }
 
 // kf.predict(u); kf.update(z) of filterpy 1.4.5 as restated in oracle/ukf_ref.py (R = 0).
-__device__ __noinline__ void ukf_step(const SimConst &c, double *x, double *P, const double *u, const double *zmeas) {
+// Returns false when a Cholesky pivot had to be clamped (the reference would have raised).
+__device__ __noinline__ bool ukf_step(const SimConst &c, double *x, double *P, const double *u, const double *zmeas) {
   double sig[78], sf[78];
-  sigma_points(x, P, sig);
+  bool ok = sigma_points(x, P, sig);
   for (int k = 0; k < 13; ++k)
     for (int i = 0; i < 6; ++i) {
       double acc = 0.0;
@@ -108,7 +117,7 @@ __device__ __noinline__ void ukf_step(const SimConst &c, double *x, double *P, c
       for (int k = 0; k < 13; ++k) acc += (k == 0 ? UKF_WC0 : UKF_WI) * (sf[k * 6 + i] - xm[i]) * (sf[k * 6 + j] - xm[j]);
       Pm[i * 6 + j] = acc + c.Qw[i * 6 + j];
     }
-  sigma_points(xm, Pm, sf);                 // filterpy 1.4.5 regenerates the points after predict
+  ok &= sigma_points(xm, Pm, sf);           // filterpy 1.4.5 regenerates the points after predict
   double zs[26], zp[2] = {0.0, 0.0};
   for (int k = 0; k < 13; ++k) {
     const double a = sf[k * 6], b = sf[k * 6 + 1];
@@ -143,6 +152,7 @@ __device__ __noinline__ void ukf_step(const SimConst &c, double *x, double *P, c
     const double ks0 = K[i * 2] * S[0] + K[i * 2 + 1] * S[2], ks1 = K[i * 2] * S[1] + K[i * 2 + 1] * S[3];
     for (int j = 0; j < 6; ++j) P[i * 6 + j] = Pm[i * 6 + j] - (ks0 * K[j * 2] + ks1 * K[j * 2 + 1]);
   }
+  return ok;
 }
 
 __device__ __forceinline__ bool terminated(const SimConst &c, const double *x) {
@@ -227,7 +237,7 @@ __device__ __forceinline__ int estimate_and_refresh(const PostArgs &a, int ln, c
     for (int i = 0; i < 6; ++i) ux[i] = a.ls.ux[i * B + ln];
     for (int i = 0; i < 36; ++i) uP[i] = a.ls.uP[i * B + ln];
     const double zm[2] = {sqrt(xn[0] * xn[0] + xn[1] * xn[1]), atan2(xn[1], xn[0])};
-    ukf_step(a.sc, ux, uP, uprev, zm);
+    if (!ukf_step(a.sc, ux, uP, uprev, zm)) a.ls.ukf_clamp[ln] = 1;
     for (int i = 0; i < 6; ++i) a.ls.ux[i * B + ln] = ux[i];
     for (int i = 0; i < 36; ++i) a.ls.uP[i * B + ln] = uP[i];
     for (int i = 0; i < 6; ++i) xe[i] = ux[i];
@@ -452,7 +462,7 @@ __global__ void post_kernel(const __grid_constant__ PostArgs a) {
 }
 
 // Final per-lane results + batch statistics (test/disturbRejComp.py:87-100, success_rates_test.py:66-75).
-__global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__restrict__ stats /*[8]*/,
+__global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__restrict__ stats /*[10]*/,
                                 const int *__restrict__ flip) {
   const int ln = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t B = a.B;
@@ -475,6 +485,9 @@ __global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__re
     v[4] = it;
     v[5] = a.ls.nsolve[ln];
     if (flip[ln]) atomicAdd(&stats[7], 1.0);
+    if (a.out.ukf_clamped) a.out.ukf_clamped[ln] = a.ls.ukf_clamp[ln];
+    if (a.ls.ukf_clamp[ln]) atomicAdd(&stats[8], 1.0);
+    if (it < ((a.mode == MODE_CONTINUOUS) ? a.n_sub_total : a.nsteps)) atomicAdd(&stats[9], 1.0);
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {

@@ -131,7 +131,9 @@ class BatchSimRun:
     status: Optional[np.ndarray] = None
     iters: Optional[np.ndarray] = None
     u_raw: Optional[np.ndarray] = None
+    ukf_clamped: Optional[np.ndarray] = None     # [B] 1 where the reference's UKF would have raised LinAlgError
     stats: dict = field(default_factory=dict)
+    stats_vec: Optional[np.ndarray] = None       # the MPCB_NSTATS doubles ranks all-reduce (sum)
 
     @property
     def batch(self) -> int:

@@ -21,6 +21,7 @@ from .osqp_ref import (ruiz_scale, OSQP_INFTY, MIN_SCALING, RHO_MIN, RHO_MAX, RH
                        OSQP_DIVISION_TOL, OSQP_SOLVED, OSQP_SOLVED_INACCURATE, OSQP_PRIMAL_INFEASIBLE,
                        OSQP_PRIMAL_INFEASIBLE_INACCURATE, OSQP_MAX_ITER_REACHED, OSQP_UNSOLVED, DEFAULT_SETTINGS)
 from .sim_ref import build_setup
+from .ukf_ref import cholesky_psd_clamp
 
 
 def _ninf(a):
@@ -193,7 +194,8 @@ class BatchedQP:
         self.rho[g[ch]] = est[ch]
 
 
-def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=None, regen_sigmas=True, nsteps=None):
+def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=None, regen_sigmas=True, nsteps=None,
+                            chol_fail='raise'):
     """Batched ``trajectorySimulate`` (debris-free).  ``x0_batch[B,4]``; ``noise_batch[R,2,B]``
     holds sigma-scaled position disturbances, refreshed every ``noise_length`` steps
     (R >= nsim//noise_length + 1).  Returns a dict of SoA arrays."""
@@ -236,8 +238,23 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
     Wm[0] = lam_u / (6 + lam_u)
     Wc[0] = Wm[0] + (1 - 0.01 + 2.0)
 
-    def sigmas(x, P):
-        U = np.linalg.cholesky((6 + lam_u) * P).transpose(0, 2, 1)     # upper, rows U[k]
+    clamped = np.zeros(B, bool)
+
+    def sigmas(x, P, idx):
+        try:
+            U = np.linalg.cholesky((6 + lam_u) * P).transpose(0, 2, 1)     # upper, rows U[k]
+        except np.linalg.LinAlgError:
+            # filterpy/scipy raise here and the reference run dies; with chol_fail='clamp' the lane
+            # continues on the positive semi-definite factor like the engine (oracle/ukf_ref.py)
+            if chol_fail != 'clamp':
+                raise
+            U = np.empty_like(P)
+            for k in range(P.shape[0]):
+                try:
+                    U[k] = np.linalg.cholesky((6 + lam_u) * P[k]).T
+                except np.linalg.LinAlgError:
+                    U[k], _ = cholesky_psd_clamp((6 + lam_u) * P[k])
+                    clamped[idx[k]] = True
         return np.concatenate([x[:, None, :], x[:, None, :] + U, x[:, None, :] - U], axis=1)
 
     def set_qp(idx, xe):
@@ -276,13 +293,13 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
         xn = xt[idx] @ Ad.T + up @ Bd.T + noise[idx]
         xtrue[i + 1, idx] = xn
         if has_noise:
-            sg = sigmas(ux[idx], uP[idx])
+            sg = sigmas(ux[idx], uP[idx], idx)
             sf = sg @ Ao.T + (up @ Bou.T)[:, None, :]
             xm = np.einsum('k,bkj->bj', Wm, sf)
             dfx = sf - xm[:, None, :]
             Pm = np.einsum('k,bki,bkj->bij', Wc, dfx, dfx) + Qw[None]
             if regen_sigmas:
-                sf = sigmas(xm, Pm)
+                sf = sigmas(xm, Pm, idx)
             zs = np.stack([np.hypot(sf[:, :, 0], sf[:, :, 1]), np.arctan2(sf[:, :, 1], sf[:, :, 0])], axis=2)
             zp = np.einsum('k,bkj->bj', Wm, zs)
             dz = zs - zp[:, None, :]
@@ -304,4 +321,4 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
         if has_noise and (i + 1) % nrep == 0:
             noise[:, :2] = noise_batch[(i + 1) // nrep].T
     return dict(i_term=iterm, x_true=xtrue, x_est=xest, ctrl_hist=ctrls, ctrlr_seq=seq, status=status, iters=iters,
-                u_raw=u_raw, rho=qp.rho.copy(), flip_flag=qp.flip_flag.copy())
+                u_raw=u_raw, rho=qp.rho.copy(), flip_flag=qp.flip_flag.copy(), ukf_clamped=clamped)

@@ -16,7 +16,10 @@ Extra, oracle-only knobs (all default to the reference's behaviour):
   * ``draw``: callable returning 4 standard normals (reference: numpy legacy global RNG,
     re-seeded with 123 on every discrete call, ``trajectorySimulate.py:28,268,352``);
   * ``solver_settings``: dict merged into the OSQP settings;
-  * ``integrator``: 'rk45' (= ``solve_ivp`` defaults, reference) or 'rk4' (fixed step h=T_cont).
+  * ``integrator``: 'rk45' (= ``solve_ivp`` defaults, reference) or 'rk4' (fixed step h=T_cont);
+  * ``chol_fail``: 'raise' (reference: scipy's Cholesky raises LinAlgError when the UKF covariance,
+    singular because R = 0, rounds to a non-positive pivot -- about 2 % of randomly placed lanes) or
+    'clamp' (the engine's continuation on the semi-definite factor, ``oracle/ukf_ref.py``).
 """
 import math
 from types import SimpleNamespace
@@ -271,7 +274,7 @@ def build_setup(sc, mp, fp, debris, use_sympy=False):
     return s
 
 
-def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas):
+def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas, chol_fail='raise'):
     """trajectorySimulate.py:121-130, 250, 272-282 (UKF model, P0, Q, R)."""
     Ao, Bou = s.Ao, s.Bou
 
@@ -281,7 +284,7 @@ def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas):
     def hx(x):
         return np.array([np.linalg.norm(x[:2]), math.atan2(x[1], x[0])])
 
-    pts = MerweScaledSigmaPointsRef(6, alpha=0.1, beta=2., kappa=-1)
+    pts = MerweScaledSigmaPointsRef(6, alpha=0.1, beta=2., kappa=-1, chol_fail=chol_fail)
     Bnoise = np.vstack([np.zeros([s.nx, s.ndi]), Bnoise_scale * np.eye(s.ndi)])
     Qw = np.diag([s.sigMat[0, 0] ** 2, s.sigMat[1, 1] ** 2])
     Qw = Bnoise @ Qw @ Bnoise.T
@@ -343,7 +346,7 @@ def _legacy_draw():
 
 # --------------------------------------------------------------------------- discrete
 def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, regen_sigmas=True,
-                        use_sympy=False, max_steps=None):
+                        use_sympy=False, max_steps=None, chol_fail='raise'):
     """trajectorySimulate.py:17-388.  Returns a SimRun-like namespace plus per-step solver
     telemetry (``status_val``, ``iters``, ``rho``, ``u_raw``) used by the parity tests."""
     if draw is None:
@@ -374,7 +377,7 @@ def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, reg
     xestO[:, 0] = xest0
     noiseVec = s.sigMat @ draw()
     noiseStored[:, 0] = noiseVec
-    kf, _ = _make_ukf(s, xest0, s.T, regen_sigmas)
+    kf, _ = _make_ukf(s, xest0, s.T, regen_sigmas, chol_fail)
 
     status_val = np.zeros(nsim, int)
     iters = np.zeros(nsim, int)
@@ -424,7 +427,8 @@ def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, reg
     seq[ifailsd] = 3
     return SimpleNamespace(i_term=iterm, isSuccess=succ, x_true_pcw=xtruePiece, x_est=xestO, ctrl_hist=ctrls,
                            ctrlr_seq=seq, noise_hist=noiseStored, x_true=xtrueP, status_val=status_val[:iterm],
-                           iters=iters[:iterm], rho=rhos[:iterm], u_raw=u_raw[:, :iterm], setup=s)
+                           iters=iters[:iterm], rho=rhos[:iterm], u_raw=u_raw[:, :iterm], setup=s,
+                           ukf_clamped=kf.points.clamped)
 
 
 # --------------------------------------------------------------------------- continuous
@@ -450,7 +454,7 @@ def _substep(x, u, n, t, h, integrator):
 
 
 def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, regen_sigmas=True,
-                          integrator='rk45', use_sympy=False):
+                          integrator='rk45', use_sympy=False, chol_fail='raise'):
     """trajectorySimulateC.py:17-446.  ``V`` (2 x n_refresh) replaces the ``ct.white_noise``
     draw (:301) when given.  The loop's literal start index 500 (:325) is restated as
     ``int(T/T_cont)``, which is what it equals for every shipped parameter set."""
@@ -491,7 +495,7 @@ def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, rege
     for j, col in enumerate(V.T):
         noiseStored[:, j * noiseIntC:noiseIntC * (1 + j)] = np.vstack([col.reshape(ndi, 1), np.zeros([2, 1])])
         sum_vec[:, j * noiseRepeat:noiseRepeat * (1 + j)] = ratio * np.concatenate([col, np.zeros(2)]).reshape(-1, 1)
-    kf, _ = _make_ukf(s, xest0, T * ratio, regen_sigmas)
+    kf, _ = _make_ukf(s, xest0, T * ratio, regen_sigmas, chol_fail)
 
     status_val, iters, u_raw, solve_at = [], [], [], []
     disc_j = 1
@@ -557,4 +561,4 @@ def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, rege
     return SimpleNamespace(i_term=iterm, isSuccess=succ, x_true_pcw=xtruePiece, x_est=xestO, ctrl_hist=ctrls,
                            ctrlr_seq=seq, noise_hist=sum_vec, x_true=xtrueP, status_val=np.array(status_val),
                            iters=np.array(iters), u_raw=np.array(u_raw).T if u_raw else np.zeros((2, 0)),
-                           solve_at=np.array(solve_at), n_est=disc_j, setup=s)
+                           solve_at=np.array(solve_at), n_est=disc_j, setup=s, ukf_clamped=kf.points.clamped)

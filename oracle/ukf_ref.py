@@ -15,9 +15,31 @@ import numpy as np
 import scipy.linalg as sla
 
 
+def cholesky_psd_clamp(M):
+    """Upper factor ``U'U = M`` that never raises: a pivot <= 0 leaves that row of U zero.
+    NOT filterpy behaviour (scipy.linalg.cholesky raises LinAlgError there and the reference run
+    dies); it is the engine's documented continuation for such lanes, restated here so that the
+    parity tests can cover them.  Returns (U, clamped)."""
+    n = M.shape[0]
+    U = np.zeros((n, n))
+    clamped = False
+    for i in range(n):
+        d = M[i, i] - U[:i, i] @ U[:i, i]
+        if not d > 0.0:
+            clamped = True
+            continue
+        r = np.sqrt(d)
+        U[i, i] = r
+        for j in range(i + 1, n):
+            U[i, j] = (M[i, j] - U[:i, i] @ U[:i, j]) / r
+    return U, clamped
+
+
 class MerweScaledSigmaPointsRef:
-    def __init__(self, n, alpha, beta, kappa):
+    def __init__(self, n, alpha, beta, kappa, chol_fail='raise'):
         self.n, self.alpha, self.beta, self.kappa = n, alpha, beta, kappa
+        self.chol_fail = chol_fail          # 'raise' = filterpy/scipy; 'clamp' = engine continuation
+        self.clamped = False
         lam = alpha ** 2 * (n + kappa) - n
         c = 0.5 / (n + lam)
         self.Wc = np.full(2 * n + 1, c)
@@ -28,7 +50,13 @@ class MerweScaledSigmaPointsRef:
 
     def sigma_points(self, x, P):
         n = self.n
-        U = sla.cholesky((self.lam + n) * P)       # upper, U'U = (n+lam) P
+        try:
+            U = sla.cholesky((self.lam + n) * P)   # upper, U'U = (n+lam) P
+        except np.linalg.LinAlgError:
+            if self.chol_fail != 'clamp':
+                raise
+            U, _ = cholesky_psd_clamp((self.lam + n) * P)
+            self.clamped = True
         sig = np.zeros((2 * n + 1, n))
         sig[0] = x
         for k in range(n):

@@ -1,0 +1,279 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the CPU oracle on identical
+inputs, and against the fixtures captured from the reference's own driver code.
+
+Tolerances.  The ADMM iterates are float64 on both sides; the engine and the oracle differ only
+in summation order, so discrete decisions (iteration counts, OSQP status, controller choice,
+termination step) must agree exactly on these seeds, controls to 1e-6 abs (task bound: 1e-4)
+and closed-loop states to 1e-6 abs / 1e-7 rel.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import mpc_arpo_project_b200 as M
+from oracle.gen_golden import CASES as GOLDEN_CASES, make_params
+from oracle.batched_ref import BatchedQP, simulate_discrete_batch
+from oracle.sim_ref import build_setup, trajectory_simulate, trajectory_simulate_c, state_eqn_n
+from oracle.ukf_ref import UKFRef, MerweScaledSigmaPointsRef
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+U_ATOL = 1e-6
+X_ATOL, X_RTOL = 1e-6, 1e-7
+
+
+def lanes(case, B, seed):
+    rng = np.random.default_rng(seed)
+    base = np.array([-10., 100., 0, 0]) if case.get('inTrack') else np.array([100., 10., 0, 0])
+    x0 = base[None, :] + np.concatenate([rng.uniform(-5, 5, (B, 2)), np.zeros((B, 2))], axis=1)
+    return x0, rng
+
+
+# ------------------------------------------------------------------------------------ QP seam
+@pytest.mark.parametrize("Nx", [10, 20, 30, 40])
+def test_qp_solve_cold_and_warm(Nx):
+    """mpcb_qp_solve == prob.update(l,u); prob.update(Ax,l,u); prob.solve() lane by lane."""
+    case = dict(Nx=Nx, sigma=0.1)
+    sc, mp, fp, _ = make_params(M, case)
+    B = 48
+    rng = np.random.default_rng(Nx)
+    s = build_setup(sc, mp, fp, None)
+    qp = BatchedQP(s, B)
+    eng = M.Engine(M.build_problem(sc, mp, fp, None))
+    eng.batch_alloc(B)
+    xh = np.zeros((B, 6))
+    xh[:, 0] = 100 + rng.uniform(-10, 10, B)
+    xh[:, 1] = 10 + rng.uniform(-5, 5, B)
+    for rnd in range(3):
+        if rnd:     # a plausible next-step estimate: small move, both velocity signs, a disturbance estimate
+            xh[:, :2] += rng.normal(0, 0.05, (B, 2))
+            xh[:, 2:4] = rng.normal(0, 0.1, (B, 2))
+            xh[:, 4:6] = rng.normal(0, 0.01, (B, 2))
+        val = np.abs(xh[:, 0] - s.xr[0]) + np.abs(xh[:, 1] - s.xr[1])
+        var = (xh[:, 2] < 0).astype(int) + 2 * (xh[:, 3] < 0).astype(int)
+        idx = np.arange(B)
+        qp.set_params(idx, xh[:, :4], val, xh[:, 4:6], var)
+        st_ref, it_ref = qp.solve(idx)
+        u_ref = qp.x[:, s.Nx * 4 + 4:s.Nx * 4 + 6] * qp.D[s.Nx * 4 + 4:s.Nx * 4 + 6][None, :]
+        u0, st, it = eng.qp_solve(np.ascontiguousarray(xh.T))
+        assert np.array_equal(it, it_ref), f"round {rnd}"
+        assert np.array_equal(st, st_ref), f"round {rnd}"
+        np.testing.assert_allclose(u0.T, u_ref, rtol=0, atol=U_ATOL)
+        x, z, y, rho = eng.qp_state(B // 2)
+        np.testing.assert_allclose(x, qp.x[B // 2], rtol=1e-7, atol=1e-6)      # scaled iterates, O(1e2) entries
+        np.testing.assert_allclose(y, qp.y[B // 2], rtol=1e-6, atol=1e-6)
+        assert rho == pytest.approx(qp.rho[B // 2], rel=1e-9)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------ unit seams
+def test_ukf_step_matches_oracle():
+    sc, mp, fp, _ = make_params(M, dict(Nx=10, sigma=0.75))
+    prob = M.build_problem(sc, mp, fp, None)
+    eng = M.Engine(prob)
+    B = 257
+    rng = np.random.default_rng(3)
+    x = np.zeros((6, B))
+    x[0] = 100 + rng.uniform(-10, 10, B)
+    x[1] = 10 + rng.uniform(-5, 5, B)
+    x[2:4] = rng.normal(0, 0.2, (2, B))
+    P = np.zeros((36, B))
+    for i in range(6):
+        P[i * 7] = 1e-20 if i < 4 else 1.0
+    u = rng.uniform(-0.2, 0.2, (2, B))
+    pts = MerweScaledSigmaPointsRef(6, alpha=0.1, beta=2., kappa=-1)
+    xg, Pg = x, P
+    xr_, Pr_ = x.copy(), P.copy()
+    for step in range(4):
+        xt = prob.Ad @ xg[:4] + prob.Bd @ u + rng.normal(0, 0.3, (4, B)) * np.array([1, 1, 0, 0])[:, None]
+        z = np.stack([np.hypot(xt[0], xt[1]), np.arctan2(xt[1], xt[0])])
+        xg, Pg = eng.ukf_step(xg, Pg, u, z)
+        for b in range(0, B, 16):
+            kf = UKFRef(6, 2, lambda s_, uu: prob.Ao @ s_ + prob.Bou @ uu,
+                        lambda s_: np.array([np.hypot(s_[0], s_[1]), np.arctan2(s_[1], s_[0])]), pts)
+            kf.x, kf.P, kf.Q, kf.R = xr_[:, b].copy(), Pr_[:, b].reshape(6, 6).copy(), prob.Qw, np.zeros((2, 2))
+            kf.predict(u[:, b])
+            kf.update(z[:, b])
+            np.testing.assert_allclose(xg[:, b], kf.x, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(Pg[:, b].reshape(6, 6), kf.P, rtol=1e-7, atol=1e-12)
+        xr_, Pr_ = xg.copy(), Pg.copy()
+    eng.close()
+
+
+def test_plant_steps_match_oracle():
+    sc, mp, fp, _ = make_params(M, dict(Nx=10, sigma=0.1))
+    prob = M.build_problem(sc, mp, fp, None)
+    eng = M.Engine(prob)
+    B = 300
+    rng = np.random.default_rng(4)
+    x = np.stack([100 + rng.uniform(-10, 10, B), 10 + rng.uniform(-5, 5, B), rng.normal(0, .2, B), rng.normal(0, .2, B)])
+    u = rng.uniform(-0.2, 0.2, (2, B))
+    w = rng.normal(0, 0.1, (2, B))
+    got = eng.plant_lin_step(x, u, w)
+    ref = prob.Ad @ x + prob.Bd @ u + np.vstack([w, np.zeros((2, B))])
+    np.testing.assert_allclose(got, ref, rtol=1e-14, atol=1e-13)
+    # RK4 substeps of the nonlinear plant (trajectorySimulateC.py:64-79)
+    nsub, h = 50, 1e-3
+    got = eng.plant_rk4(x, u, w * 1e-3, nsub, h)
+    ref = x.copy()
+    for b in range(0, B, 25):
+        xb = x[:, b].copy()
+        for _ in range(nsub):
+            k1 = state_eqn_n(xb, u[:, b], prob.mean_mtn)
+            k2 = state_eqn_n(xb + 0.5 * h * k1, u[:, b], prob.mean_mtn)
+            k3 = state_eqn_n(xb + 0.5 * h * k2, u[:, b], prob.mean_mtn)
+            k4 = state_eqn_n(xb + h * k3, u[:, b], prob.mean_mtn)
+            xb = xb + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+            xb[:2] += w[:, b] * 1e-3
+        np.testing.assert_allclose(got[:, b], xb, rtol=1e-12, atol=1e-11)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------ closed loops
+DISCRETE = {
+    "radial_nx10_sigma0.1": (dict(Nx=10, sigma=0.1, noise_length=5, T_final=20), 96),
+    "radial_nx10_sigma0.75": (dict(Nx=10, sigma=0.75, noise_length=50, T_final=25), 96),
+    "radial_nx10_nonoise": (dict(Nx=10, sigma=None, T_final=20), 40),
+    "intrack_dv_nx20": (dict(Nx=20, inTrack=True, isDeltaV=True, isReject=False, sigma=None, T_final=15), 40),
+    "radial_nx30_norej": (dict(Nx=30, sigma=0.7, noise_length=10, isReject=False, T_final=12), 40),
+    "radial_nx40_sigma0.3": (dict(Nx=40, sigma=0.3, noise_length=7, T_final=8), 33),
+}
+
+
+def _compare_batch(got, ref, B):
+    assert np.array_equal(got.i_term, ref['i_term'])
+    assert np.array_equal(got.iters.astype(int), ref['iters'])
+    assert np.array_equal(got.status.astype(int), ref['status'])
+    assert np.array_equal(got.ctrlr_seq, ref['ctrlr_seq'])
+    for b in range(B):
+        T = int(ref['i_term'][b])
+        np.testing.assert_allclose(got.ctrl_hist[:, :T + 1, b].T, ref['ctrl_hist'][:T + 1, b], rtol=0, atol=U_ATOL)
+        np.testing.assert_allclose(got.u_raw[:, :T, b].T, ref['u_raw'][:T, b], rtol=0, atol=U_ATOL)
+        np.testing.assert_allclose(got.x_true[:, :T + 1, b].T, ref['x_true'][:T + 1, b], rtol=X_RTOL, atol=X_ATOL)
+        np.testing.assert_allclose(got.x_est[:, :T + 1, b].T, ref['x_est'][:T + 1, b], rtol=X_RTOL, atol=X_ATOL)
+
+
+@pytest.mark.parametrize("name", list(DISCRETE))
+def test_discrete_closed_loop_matches_batched_oracle(name):
+    case, B = DISCRETE[name]
+    x0, rng = lanes(case, B, 11)
+    sc, mp, fp, _ = make_params(M, case)
+    nsim = int(case['T_final'] / 0.5)
+    sig = case.get('sigma') or 0.0
+    nl = case.get('noise_length', 50)
+    noise = sig * rng.standard_normal((nsim // nl + 1, 2, B))
+    got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise if sig else None)
+    ref = simulate_discrete_batch(sc, mp, fp, x0, noise, chol_fail='clamp')
+    _compare_batch(got, ref, B)
+    # lanes where the reference's UKF would have raised (singular posterior, R = 0): same set
+    assert np.array_equal(got.ukf_clamped.astype(bool), ref['ukf_clamped'])
+    assert int(got.stats['qp_solves']) == int(ref['i_term'].sum())
+    assert int(got.stats['admm_iterations']) == int(ref['iters'].sum())
+
+
+def test_discrete_closed_loop_matches_scalar_oracle():
+    """Three lanes against oracle/sim_ref.trajectory_simulate (OSQP-shaped KKT solve, per-step
+    re-scaling and refactorisation like the real package)."""
+    case = dict(Nx=10, sigma=0.4, noise_length=6, T_final=15)
+    B = 3
+    x0, rng = lanes(case, B, 5)
+    sc, mp, fp, _ = make_params(M, case)
+    nsim = 30
+    draws = rng.standard_normal((B, nsim + 2, 4))
+    noise = np.ascontiguousarray((0.4 * draws[:, :nsim // 6 + 1, :2]).transpose(1, 2, 0))
+    got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
+    for b in range(B):
+        sc.x0 = x0[b].copy()
+        it = iter(draws[b])
+        r = trajectory_simulate(sc, mp, fp, None, draw=lambda: next(it), chol_fail='clamp')
+        T = r.i_term
+        assert got.i_term[b] == T
+        assert list(got.iters[:T, b]) == list(r.iters)
+        assert list(got.status[:T, b]) == list(r.status_val)
+        np.testing.assert_allclose(got.ctrl_hist[:, :T + 1, b], r.ctrl_hist[:, :T + 1], rtol=0, atol=U_ATOL)
+        np.testing.assert_allclose(got.x_true[:, :T + 1, b], r.x_true[:, :T + 1], rtol=X_RTOL, atol=X_ATOL)
+        np.testing.assert_allclose(got.x_est[:, :T + 1, b], r.x_est[:, :T + 1], rtol=X_RTOL, atol=X_ATOL)
+        assert bool(got.isSuccess[b]) == bool(r.isSuccess)
+
+
+@pytest.mark.parametrize("name", [k for k, v in GOLDEN_CASES.items() if v[0] == 'D' and not v[1].get('debris')])
+def test_drop_in_matches_reference_driver_fixture(name):
+    """trajectorySimulate(...) -> SimRun against the fixture captured from the reference's
+    src/trajectorySimulate.py (same legacy-RNG noise, seed 123)."""
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"), allow_pickle=False)
+    sc, mp, fp, debris = make_params(M, GOLDEN_CASES[name][1])
+    r = M.trajectorySimulate(sc, mp, fp, debris)
+    it = int(g["i_term"])
+    assert r.i_term == it
+    assert bool(r.isSuccess) == bool(g["isSuccess"])
+    assert r.x_true_pcw.shape == g["x_true_pcw"].shape and r.x_est.shape == g["x_est"].shape
+    assert r.ctrl_hist.shape == g["ctrl_hist"].shape and r.ctrlr_seq.shape == g["ctrlr_seq"].shape
+    np.testing.assert_allclose(r.ctrl_hist[:, :it + 1], g["ctrl_hist"][:, :it + 1], rtol=0, atol=U_ATOL)
+    np.testing.assert_allclose(r.x_true_pcw, g["x_true_pcw"], rtol=X_RTOL, atol=X_ATOL)
+    np.testing.assert_allclose(r.x_est[:, :it + 1], g["x_est"][:, :it + 1], rtol=X_RTOL, atol=X_ATOL)
+    np.testing.assert_array_equal(r.ctrlr_seq, g["ctrlr_seq"])
+    np.testing.assert_allclose(r.noise_hist[:, :it + 1], g["noise_hist"][:, :it + 1], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dv", [False, True])
+def test_continuous_closed_loop_matches_scalar_oracle(dv):
+    case = dict(Nx=10, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=3, isDeltaV=dv)
+    B = 2
+    x0, rng = lanes(case, B, 9)
+    sc, mp, fp, _ = make_params(M, case)
+    nsimD, nsimC, ratio = 6, 3000, 500
+    n_refresh = np.arange(0, 3, 0.5 * 4).size
+    V = 0.0012 * rng.standard_normal((B, 2, n_refresh))
+    noise = np.ascontiguousarray(V.transpose(2, 1, 0))
+    got = M.trajectorySimulateCBatch(sc, mp, fp, None, x0, noise)
+    for b in range(B):
+        sc.x0 = x0[b].copy()
+        r = trajectory_simulate_c(sc, mp, fp, None, V=V[b], integrator='rk4', chol_fail='clamp')
+        assert got.i_term[b] == r.i_term
+        ns = len(r.iters)
+        assert list(got.iters[:ns, b]) == list(r.iters)
+        assert list(got.status[:ns, b]) == list(r.status_val)
+        np.testing.assert_allclose(got.u_raw[:, :ns, b], r.u_raw, rtol=0, atol=U_ATOL)
+        np.testing.assert_allclose(got.x_est[:, :r.n_est, b], r.x_est[:, :r.n_est], rtol=X_RTOL, atol=X_ATOL)
+        # column j+1 of x_true: the plant state right after the j-th solve's substep
+        for j, i_sub in enumerate(r.solve_at):
+            np.testing.assert_allclose(got.x_true[:, j + 1, b], r.x_true[:, i_sub + 1], rtol=X_RTOL, atol=X_ATOL)
+        assert bool(got.isSuccess[b]) == bool(r.isSuccess)
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_full_size_config2_properties():
+    """BASELINE config 2 (4096 lanes, Nx=10, sigma=0.75 held 50 steps, 300 steps): size-independent
+    properties -- the recorded trajectory replays through the plant model from the recorded controls
+    and noise; applied controls respect the (component-wise effective) clip; lanes are independent of their position in
+    the batch (duplicated lanes give bit-identical results)."""
+    case = dict(Nx=10, sigma=0.75, noise_length=50, T_final=150)
+    sc, mp, fp, _ = make_params(M, case)
+    B, nsim = 4096, 300
+    rng = np.random.default_rng(1234)
+    x0 = np.stack([100 + rng.uniform(-10, 10, B), 10 + rng.uniform(-5, 5, B), np.zeros(B), np.zeros(B)], axis=1)
+    noise = 0.75 * rng.standard_normal((7, 2, B))
+    x0[B // 2:] = x0[:B // 2][::-1]                 # second half = first half, reversed order
+    noise[:, :, B // 2:] = noise[:, :, :B // 2][:, :, ::-1]
+    got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
+    prob = M.build_problem(sc, mp, fp, None)
+    it = got.i_term
+    assert it.min() >= 1 and it.max() <= nsim
+    assert np.array_equal(it[B // 2:], it[:B // 2][::-1])
+    assert np.array_equal(got.ctrl_hist[:, :, B // 2:], got.ctrl_hist[:, :, :B // 2][:, :, ::-1], equal_nan=True)
+    assert np.array_equal(got.x_true[:, :, B // 2:], got.x_true[:, :, :B // 2][:, :, ::-1], equal_nan=True)
+    steps = np.arange(nsim)[:, None]
+    live = steps < it[None, :]                                  # [nsim, B] step i executed
+    # the reference's clip is sequential (u0 scaled by the norm, then u1 by the NEW norm, :317-319):
+    # it bounds each component, not the norm
+    assert np.all(np.abs(got.ctrl_hist[:, 1:][:, live]) <= 0.2 * (1 + 1e-12))
+    w = noise[np.minimum(np.arange(nsim) // 50, 6)]             # [nsim, 2, B]
+    pred = np.einsum('ij,jtb->itb', prob.Ad, got.x_true[:, :-1]) + np.einsum('ij,jtb->itb', prob.Bd, got.ctrl_hist[:, :-1])
+    pred[:2] += w.transpose(1, 0, 2)
+    err = np.abs(pred - got.x_true[:, 1:])
+    assert np.nanmax(np.where(live[None], err, 0.0)) < 1e-9
+    assert int(got.stats['qp_solves']) == int(it.sum())
+    assert set(np.unique(got.ctrlr_seq[live])) <= {1, 2}
+    assert int(got.stats['flip_lanes']) == 0
