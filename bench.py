@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the batched closed-loop MPC engine (BASELINE.json metric: closed-loop MPC QP
+solves per second = live trajectory control steps per second).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2] [--impl b200|reference]
+
+One "step" = one full pass of the hot path over one batch: a whole closed-loop simulation of the
+workload (config2 = 4096 linear-CW radial trajectories, 10-step horizon, 300 control steps, one QP
+per live trajectory per control step).  For N > 1 the driver launches this file under torchrun;
+every rank runs its own shard of lanes (weak scaling, seeds 1234 + rank) and the only collective is
+an NCCL all-reduce of the MPCB_NSTATS final statistics.
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "closed-loop MPC QP solves/sec (traj-steps/s)"
+UNIT = "solves/s"
+
+# SURVEY.md section 8(d) synthetic workloads.  lanes = per-GPU shard.
+WORKLOADS = {
+    "config2": dict(kind="D", lanes=4096, case=dict(Nx=10, sigma=0.75, noise_length=50, T_final=150),
+                    desc="trajectorySimulate batched: 4096 linear-CW radial lanes, Nx=10, sigma=0.75 held 50 steps, 300 steps"),
+    "config2_quiet": dict(kind="D", lanes=4096, case=dict(Nx=10, sigma=0.1, noise_length=50, T_final=150),
+                          desc="config2 with sigma=0.1 (MPC stays feasible: solver-throughput variant)"),
+    "config3": dict(kind="C", lanes=65536, case=dict(Nx=10, sigma=0.0012, noise_length=50, T_cont=0.001, T_final=150),
+                    desc="trajectorySimulateC batched: 65536 nonlinear-plant lanes, accel inputs, RK4 h=1ms"),
+    "config4": dict(kind="D", lanes=32768, case=dict(Nx=20, inTrack=True, isDeltaV=True, isReject=False, sigma=None, T_final=150),
+                    desc="in-track delta-v sweep, Nx=20, 262144 lanes over 8 GPUs (32768 per GPU)"),
+    "config5": dict(kind="D", lanes=131072, case=dict(Nx=30, sigma=0.7, noise_length=50, T_final=150),
+                    desc="disturbRejComp Monte Carlo cell, Nx=30, 1M lanes over 8 GPUs (131072 per GPU)"),
+}
+
+
+def f_it(n, m, nnzA):
+    """Algorithmic flops per ADMM iteration per trajectory, SURVEY.md section 8(d): 2n^2 + 4 nnz(A) + 12 m + 8 n."""
+    return 2 * n * n + 4 * nnzA + 12 * m + 8 * n
+
+
+def make_inputs(wl, B, seed):
+    """Synthetic lanes of SURVEY.md 8(d): x0 = nominal + U(-10,10) x U(-5,5); N(0,1)*sigma disturbances."""
+    case = wl["case"]
+    rng = np.random.default_rng(seed)
+    if case.get("inTrack"):
+        x0 = np.stack([rng.uniform(-15, 15, B), 100 + rng.uniform(-10, 10, B), np.zeros(B), np.zeros(B)])
+    else:
+        x0 = np.stack([100 + rng.uniform(-10, 10, B), 10 + rng.uniform(-5, 5, B), np.zeros(B), np.zeros(B)])
+    sig = case.get("sigma")
+    noise = None
+    if sig:
+        T, Tf, nl = 0.5, case["T_final"], case["noise_length"]
+        R = (int(Tf / T) // nl + 1) if wl["kind"] == "D" else np.arange(0, Tf, T * nl).size
+        noise = sig * rng.standard_normal((R, 2, B))
+    return np.ascontiguousarray(x0), noise
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={uuid}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples above the idle clock
+        load = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    """One trajectory of the restated reference path (oracle/sim_ref.py) -- CPU, one core."""
+    case, x0, draws = args
+    import mpc_arpo_project_b200.mpcsim as M
+    from oracle.gen_golden import make_params
+    from oracle.sim_ref import trajectory_simulate, trajectory_simulate_c
+    sc, mp, fp, _ = make_params(M, case)
+    sc.x0 = np.array(x0, float)
+    t0 = time.perf_counter()
+    if "T_cont" in case:
+        r = trajectory_simulate_c(sc, mp, fp, None, V=draws, integrator="rk4", chol_fail="clamp")
+        solves = len(r.iters)
+    else:
+        it = iter(draws)
+        r = trajectory_simulate(sc, mp, fp, None, draw=lambda: next(it, np.zeros(4)), chol_fail="clamp")
+        solves = int(r.i_term)
+    return solves, time.perf_counter() - t0
+
+
+def make_pool(cores):
+    import multiprocessing as mpx
+    if cores <= 1:
+        return None
+    # one BLAS thread per worker process: set before the children import numpy
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        pool = mpx.get_context("spawn").Pool(cores)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    pool.map(_ref_import, range(cores))          # pay the interpreter / scipy import cost outside the timing
+    return pool
+
+
+def _ref_import(_):
+    import mpc_arpo_project_b200.mpcsim  # noqa: F401
+    import oracle.sim_ref  # noqa: F401
+    import oracle.gen_golden  # noqa: F401
+    return 0
+
+
+def cpu_reference_run(wl, lanes, cores, seed=1234, pool=None):
+    """Times the oracle's restatement of the reference's per-trajectory Python loop on `cores` host
+    processes over `lanes` lanes of the workload (same x0 / noise distribution as the GPU arm)."""
+    case = dict(wl["case"])
+    x0, noise = make_inputs(wl, lanes, seed)
+    jobs = []
+    for b in range(lanes):
+        if noise is None:
+            d = np.zeros((2, 4)) if wl["kind"] == "D" else None
+        elif wl["kind"] == "D":
+            d = np.concatenate([noise[:, :, b] / case["sigma"], np.zeros((noise.shape[0], 2))], axis=1)
+        else:
+            d = noise[:, :, b].T
+        jobs.append((case, x0[:, b], d))
+    own = pool is None and cores > 1
+    if own:
+        pool = make_pool(cores)
+    t0 = time.perf_counter()
+    if pool is not None:
+        res = pool.map(_ref_worker, jobs, chunksize=1)
+    else:
+        res = [_ref_worker(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    if own:
+        pool.close()
+    solves = sum(r[0] for r in res)
+    return solves, wall
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    lanes = max(cores, args.ref_lanes)
+    vals, times, solves = [], [], 0
+    pool = make_pool(cores)
+    for i in range(args.warmup + args.steps):
+        s, w = cpu_reference_run(wl, lanes, cores, seed=1234 + i, pool=pool)
+        if i >= args.warmup:
+            vals.append(s / w)
+            times.append(w)
+            solves += s
+    if pool is not None:
+        pool.close()
+    value = solves / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "lanes_per_step": lanes,
+                   "note": "osqp/filterpy/control are not installable offline: this is the oracle's restatement of the "
+                           "reference's per-trajectory Python+OSQP loop (oracle/sim_ref.py), one process per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{lanes} lanes of {args.workload} per step, full horizon"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes", type=int, default=None, help="lanes per GPU (default: the workload's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-lanes", type=int, default=32, help="reference arm: lanes per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+    if args.warmup < 3:
+        print("[bench] warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+
+    import torch
+    import torch.distributed as dist
+    import mpc_arpo_project_b200 as M
+    from mpc_arpo_project_b200 import _lib
+    from mpc_arpo_project_b200.trajectorySimulateC import continuous_grid, noise_plan
+    from oracle.gen_golden import make_params          # parameter literals of the reference scripts (test infrastructure)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+
+    B = args.lanes or wl["lanes"]
+    case = wl["case"]
+    sc, mp, fp, _ = make_params(M, case)
+    if wl["kind"] == "D":
+        prob = M.build_problem(sc, mp, fp, None)
+        nsteps = int(sc.T_final / sc.time_stp)
+    else:
+        prob = M.build_problem_c(sc, mp, fp, None)
+        nsimD, nsimC, ratio = continuous_grid(sc)
+        _, hold = noise_plan(sc)
+    eng = M.Engine(prob, device=local)
+    eng.batch_alloc(B)
+    record = ("x_true", "x_est", "ctrl", "ctrlr_seq")          # the SimRun fields of the reference
+
+    x0_h, noise_h = make_inputs(wl, B, 1234 + rank)
+    # pinned host copies (e2e leg) and device-resident copies (kernel-throughput leg)
+    x0_p = torch.from_numpy(x0_h).pin_memory()
+    noise_p = torch.from_numpy(noise_h).pin_memory() if noise_h is not None else None
+    x0_d = x0_p.to(dev)
+    noise_d = noise_p.to(dev) if noise_p is not None else None
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(on_device):
+        if wl["kind"] == "D":
+            if on_device:
+                return eng.simulate_discrete(x0_d, noise_d, nsteps, record)
+            return eng.simulate_discrete(x0_p.numpy(), noise_p.numpy() if noise_p is not None else None, nsteps, record)
+        if on_device:
+            return eng.simulate_continuous(x0_d, noise_d, nsimC, ratio, float(sc.T_cont), hold, record)
+        return eng.simulate_continuous(x0_p.numpy(), noise_p.numpy() if noise_p is not None else None, nsimC, ratio,
+                                       float(sc.T_cont), hold, record)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    stats_t = torch.zeros(_lib.NSTATS, dtype=torch.float64, device=dev)
+
+    def timed(nrep, on_device):
+        """nrep steps; returns (device ms summed over steps, solves, last result).  L2 is flushed between steps."""
+        tot_ms, solves, res = 0.0, 0, None
+        for _ in range(nrep):
+            flush.fill_(1)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            res = step(on_device)
+            if world > 1:       # the only collective of the path: final statistics
+                stats_t.copy_(torch.from_numpy(res.stats_vec))
+                dist.all_reduce(stats_t)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            tot_ms += e0.elapsed_time(e1)
+            solves += int(res.stats["qp_solves"])
+        return tot_ms, solves, res
+
+    for _ in range(args.warmup):
+        step(True)
+    c0 = eng.counters()
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    sync_all()
+    ms, solves, res = timed(args.steps, True)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    c1 = eng.counters()
+
+    # end-to-end leg: same steps through the public API with pinned HOST buffers (H2D + D2H inside)
+    step(False)
+    sync_all()
+    ms_e2e, solves_e2e, res_h = timed(args.steps, False)
+    sync_all()
+    h2d = x0_h.nbytes + (noise_h.nbytes if noise_h is not None else 0)
+    d2h = sum(getattr(res_h, k).nbytes for k in ("x_true", "x_est", "ctrl_hist", "ctrlr_seq", "i_term", "isSuccess",
+                                                 "final_dist", "ukf_clamped")) + 8 * _lib.NSTATS
+
+    # roofline leg: one more device-resident step with per-launch CUDA events around the ADMM kernel
+    eng.set_timing(True)
+    t0 = eng.counters()
+    step(True)
+    t1 = eng.counters()
+    eng.set_timing(False)
+
+    red = torch.tensor([ms, float(solves), ms_e2e, float(solves_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = red.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = red.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(mx[0]), float(mx[2])
+        solves, solves_e2e = int(sm[1]), int(sm[3])
+
+    if rank == 0:
+        n, m = prob.n, prob.m
+        nnzA = int(np.count_nonzero(prob.A))
+        fit = f_it(n, m, nnzA)
+        admm_ms = t1["admm_ms"] - t0["admm_ms"]
+        admm_launches = t1["admm_launches"] - t0["admm_launches"]
+        admm_iters = t1["admm_iterations"] - t0["admm_iterations"]
+        step_ms_timed = t1["total_ms"] - t0["total_ms"]
+        peak_dfma, peak_dmma = np.zeros(1), np.zeros(1)
+        lib = _lib.load()
+        _lib.check(lib.mpcb_measure_fp64_peak(local, 0, peak_dfma.ctypes.data_as(_lib.c_double_p)))
+        _lib.check(lib.mpcb_measure_fp64_peak(local, 1, peak_dmma.ctypes.data_as(_lib.c_double_p)))
+        peak = float(max(peak_dfma[0], peak_dmma[0]))
+        achieved = fit * admm_iters / (admm_ms * 1e-3) / 1e12 if admm_ms > 0 else None
+        status = res.stats
+        line = {
+            "metric": METRIC, "value": solves / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "lanes_per_gpu": B, "Nx": prob.Nx, "n": n, "m": m,
+                       "l2": "flushed between steps (256 MiB write)", "telemetry": list(record),
+                       "solver": "OSQP-equivalent ADMM, reference defaults (eps 1e-3, adaptive rho, check every 25)",
+                       "mean_admm_iters_per_solve": status["admm_iterations"] / max(1.0, status["qp_solves"]),
+                       "live_steps_per_lane": status["qp_solves"] / B,
+                       "flip_lanes": status["flip_lanes"], "ukf_clamped_lanes": status["ukf_clamped_lanes"]},
+            "e2e": {"value": solves_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "admm_block_kernel", "algorithmic_flops_per_iteration": fit,
+                         "launches": int(admm_launches), "avg_launch_ms": admm_ms / max(1, admm_launches),
+                         "share_of_step": admm_ms / step_ms_timed if step_ms_timed else None,
+                         "peak_source": "measured live on this GPU: float64 DFMA %.1f / DMMA m8n8k4 %.1f TFLOP/s "
+                                        "(MEASURED_PEAKS.json has no float64 entry)" % (peak_dfma[0], peak_dmma[0])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            lanes = max(2 * cores, 32)
+            s, w = cpu_reference_run(wl, lanes, cores)
+            line["cpu_baseline"] = {"value": s / w, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{lanes} lanes of {args.workload}, full horizon, oracle/sim_ref.py "
+                                              f"(restated per-trajectory Python+OSQP loop), {w:.1f} s wall"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,11 @@ int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub_total, int
 #define MPCB_NSTATS 10
 int mpcb_stats(mpcb_handle *h, int64_t B, double *stats, int io_on_device);
 
+/* Bench utility (no reference counterpart): float64 peak of the device in TFLOP/s, measured with a
+ * register-resident DFMA loop (use_dmma = 0) or mma.sync.m8n8k4.f64 loop (use_dmma = 1); the roofline
+ * denominators for this float64 path (MEASURED_PEAKS.json has none). */
+int mpcb_measure_fp64_peak(int device, int use_dmma, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif
