@@ -370,7 +370,8 @@ def main():
                        "solver": "OSQP-equivalent ADMM, reference defaults (eps 1e-3, adaptive rho, check every 25)",
                        "mean_admm_iters_per_solve": status["admm_iterations"] / max(1.0, status["qp_solves"]),
                        "live_steps_per_lane": status["qp_solves"] / B,
-                       "flip_lanes": status["flip_lanes"], "ukf_clamped_lanes": status["ukf_clamped_lanes"]},
+                       "flip_lanes": status["flip_lanes"], "ukf_clamped_lanes": status["ukf_clamped_lanes"],
+                       "operator_rebuilds_per_step": (c1["operator_rebuilds"] - c0["operator_rebuilds"]) / max(1, args.steps)},
             "e2e": {"value": solves_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),

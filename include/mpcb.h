@@ -102,6 +102,7 @@ typedef struct mpcb_counters {
   int64_t admm_launches;    /* of which: ADMM block kernel */
   int64_t rounds;           /* lockstep rounds (one 25-iteration block per live lane) */
   int64_t flip_lanes;       /* lanes that hit the unsupported "E*val < RHO_TOL" row reclassification */
+  int64_t operator_rebuilds;/* per-trajectory KKT operator rebuilds (rho adapted or velocity signs flipped) */
   double admm_ms;           /* CUDA-event time spent in the ADMM block kernel (if timing enabled) */
   double total_ms;          /* CUDA-event time of the whole call, on the handle's stream */
 } mpcb_counters;

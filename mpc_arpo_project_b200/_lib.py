@@ -52,6 +52,7 @@ class MpcbCounters(C.Structure):
     _fields_ = [
         ("qp_solves", C.c_int64), ("admm_iterations", C.c_int64), ("kernel_launches", C.c_int64),
         ("admm_launches", C.c_int64), ("rounds", C.c_int64), ("flip_lanes", C.c_int64),
+        ("operator_rebuilds", C.c_int64),
         ("admm_ms", C.c_double), ("total_ms", C.c_double),
     ]
 

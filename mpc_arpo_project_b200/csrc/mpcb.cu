@@ -13,6 +13,8 @@
 #include "admm.cuh"
 #include "common.cuh"
 #include "sim.cuh"
+#include "team.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -76,6 +78,16 @@ struct mpcb_handle {
   size_t smem_bytes = 0;
   double qn_unscaled = 0, qn_scaled = 0;
   int num_sms = 148;
+  // team kernel (n = 81 family): whole closed loop per CTA, operator in registers
+  bool team_ok = false;
+  TeamHdr thdr;
+  unsigned char *d_tblob = nullptr;
+  double *d_Vk[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_lam = nullptr;
+  int *d_queue = nullptr;
+  size_t team_smem = 0;
+  const void *team_fn_ptr = nullptr;
+  int team_ctas = 0;
   // batch state
   int64_t B = 0;
   double *xs = nullptr, *zs = nullptr, *ys = nullptr, *rho = nullptr, *par = nullptr, *u0 = nullptr;
@@ -86,7 +98,7 @@ struct mpcb_handle {
   LaneSim ls;
   double *lane_f64 = nullptr;   // backing store of LaneSim doubles
   int *lane_i32 = nullptr;      // backing store of LaneSim ints
-  unsigned long long *d_tot = nullptr;   // [0] admm iterations, [1] qp solves
+  unsigned long long *d_tot = nullptr;   // [0] admm iterations, [1] qp solves, [2] operator rebuilds, [3] spare
   double *d_stats = nullptr;             // [MPCB_NSTATS]
   int *h_cnt = nullptr;                  // pinned [4]
   bool sim_done = false;
@@ -276,6 +288,213 @@ static void set_warps(mpcb_handle *h, int w) {
   h->smem_bytes = (size_t)h->hdr.total + 16 + (size_t)w * 8 * (h->hp.p.m + 2 * h->hp.p.n);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Team kernel tables: ELL in "team layout" (row r -> thread r % TEAM, slot r / TEAM; entry e of a
+// slot at [(base + e) * TEAM + thread]), the sign-patch list, k-major V per variant.
+typedef void (*team_fn)(const TeamArgs);
+struct TeamShape { int n, m, wa, wat2, wp, ss; team_fn fn; };
+static const TeamShape kTeamShapes[] = {
+  {81, 136, 8, 6, 4, 0, team_kernel<81, 136, 8, 6, 4, 0>},     // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
+};
+static const TeamShape *team_shape_for(int n, int m) {
+  for (const TeamShape &t : kTeamShapes)
+    if (t.n == n && t.m == m) return &t;
+  return nullptr;
+}
+
+static int build_team_tables(mpcb_handle *h) {
+  const HostProblem &hp = h->hp;
+  const mpcb_problem &p = hp.p;
+  const int n = p.n, m = p.m;
+  const TeamShape *ts = team_shape_for(n, m);
+  if (!ts || getenv("MPCB_FORCE_V1")) return MPCB_OK;
+  const int mp = (m + 1) & ~1, nct = ((2 * n + 31) / 32) * 32, npair = nct / 2;
+  // nnz lists: rows of A, columns of A (= rows of A'), rows of P
+  std::vector<std::vector<int>> rowsA(m), colsA(n), rowsP(n);
+  for (int r = 0; r < m; ++r)
+    for (int c = 0; c < n; ++c)
+      if (hp.A_s[(size_t)r * n + c] != 0.0) {
+        rowsA[r].push_back(c);
+        colsA[c].push_back(r);
+      }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c)
+      if (hp.P_s[(size_t)r * n + c] != 0.0) rowsP[r].push_back(c);
+  // hand out rows / columns in order of decreasing nnz so every warp gets its own ELL width
+  std::vector<int> rowmap(m), colmap(n), rowpos(m), colpos(n);
+  for (int r = 0; r < m; ++r) rowmap[r] = r;
+  for (int c = 0; c < n; ++c) colmap[c] = c;
+  std::stable_sort(rowmap.begin(), rowmap.end(), [&](int x, int y) { return rowsA[x].size() > rowsA[y].size(); });
+  std::stable_sort(colmap.begin(), colmap.end(), [&](int x, int y) { return colsA[x].size() > colsA[y].size(); });
+  for (int t = 0; t < m; ++t) rowpos[rowmap[t]] = t;
+  for (int q = 0; q < n; ++q) colpos[colmap[q]] = q;
+  TeamHdr hd;
+  memset(&hd, 0, sizeof hd);
+  for (int t = 0; t < m; ++t) {
+    const int w = (int)rowsA[rowmap[t]].size();
+    if (w > ts->wa || w > 8) return MPCB_OK;                 // wider than the instantiation: stay on the generic path
+    hd.wA[t / 32] = std::max(hd.wA[t / 32], w);
+  }
+  for (int q = 0; q < n; ++q) {
+    const int w2 = ((int)colsA[colmap[q]].size() + 1) / 2;
+    if (w2 > ts->wat2 || w2 > 8) return MPCB_OK;
+    hd.wAT2[(2 * q) / 32] = std::max(hd.wAT2[(2 * q) / 32], w2);
+    if ((int)rowsP[colmap[q]].size() > ts->wp) return MPCB_OK;
+  }
+  std::vector<double> Av((size_t)ts->wa * mp, 0.0), ATv((size_t)ts->wat2 * nct, 0.0), Pv((size_t)ts->wp * npair, 0.0);
+  std::vector<uint16_t> Ac((size_t)8 * mp, 0), ATc((size_t)8 * nct, 0), Pc((size_t)ts->wp * npair, 0), rmap(mp, 0), cmap(npair, 0);
+  for (int t = 0; t < m; ++t) {
+    const int r = rowmap[t];
+    rmap[t] = (uint16_t)r;
+    for (size_t e = 0; e < rowsA[r].size(); ++e) {
+      Av[e * mp + t] = hp.A_s[(size_t)r * n + rowsA[r][e]];
+      Ac[(size_t)t * 8 + e] = (uint16_t)rowsA[r][e];
+    }
+  }
+  for (int q = 0; q < n; ++q) {
+    const int c = colmap[q];
+    cmap[q] = (uint16_t)c;
+    for (size_t k = 0; k < colsA[c].size(); ++k) {
+      const int tid = 2 * q + (int)(k & 1);
+      ATv[(k / 2) * nct + tid] = hp.A_s[(size_t)colsA[c][k] * n + c];
+      ATc[(size_t)tid * 8 + k / 2] = (uint16_t)colsA[c][k];
+    }
+    for (size_t e = 0; e < rowsP[c].size(); ++e) {
+      Pv[e * npair + q] = hp.P_s[(size_t)c * n + rowsP[c][e]];
+      Pc[e * npair + q] = (uint16_t)rowsP[c][e];
+    }
+  }
+  std::vector<int4> patch;
+  const int nX = 4 * (p.Nx + 1);
+  for (int k = 0; k <= p.Nx; ++k) {
+    const int r = nX + 5 * k + 3;
+    for (int which = 1; which <= 2; ++which) {
+      const int c = 4 * k + 1 + which;
+      int ia = -1, iat = -1;
+      for (size_t e = 0; e < rowsA[r].size(); ++e)
+        if (rowsA[r][e] == c) ia = (int)(e * mp + rowpos[r]);
+      for (size_t kk = 0; kk < colsA[c].size(); ++kk)
+        if (colsA[c][kk] == r) iat = (int)((kk / 2) * nct + 2 * colpos[c] + (kk & 1));
+      if (ia < 0 || iat < 0) return fail(MPCB_ERR_INVALID, "velocity-sign entry missing from A");
+      patch.push_back(make_int4(ia, iat, which, 0));
+    }
+  }
+  int off = 0;
+  auto take = [&](size_t bytes) {
+    const int o = off;
+    off = align16(off + (int)bytes);
+    return o;
+  };
+  hd.off_q = take(8 * n); hd.off_D = take(8 * n); hd.off_Dinv = take(8 * n);
+  hd.off_E = take(8 * m); hd.off_Einv = take(8 * m); hd.off_lt = take(8 * m); hd.off_ut = take(8 * m);
+  hd.off_Av = take(8 * Av.size()); hd.off_ATv = take(8 * ATv.size()); hd.off_Pv = take(8 * Pv.size());
+  hd.off_Ac = take(2 * Ac.size()); hd.off_ATc = take(2 * ATc.size()); hd.off_Pc = take(2 * Pc.size());
+  hd.off_rowmap = take(2 * rmap.size()); hd.off_colmap = take(2 * cmap.size());
+  hd.off_flags = take(m);
+  hd.off_patch = take(16 * patch.size());
+  hd.n_patch = (int)patch.size();
+  hd.total = off;
+  std::vector<unsigned char> b(hd.total, 0);
+  auto putd = [&](int o, const double *src, size_t cnt) { memcpy(b.data() + o, src, cnt * 8); };
+  std::vector<double> Dinv(n), Einv(m);
+  for (int j = 0; j < n; ++j) Dinv[j] = 1.0 / hp.D[j];
+  for (int i = 0; i < m; ++i) Einv[i] = 1.0 / hp.E[i];
+  putd(hd.off_q, hp.q_s.data(), n); putd(hd.off_D, hp.D.data(), n); putd(hd.off_Dinv, Dinv.data(), n);
+  putd(hd.off_E, hp.E.data(), m); putd(hd.off_Einv, Einv.data(), m);
+  putd(hd.off_lt, hp.l_s.data(), m); putd(hd.off_ut, hp.u_s.data(), m);
+  putd(hd.off_Av, Av.data(), Av.size());
+  putd(hd.off_ATv, ATv.data(), ATv.size());
+  putd(hd.off_Pv, Pv.data(), Pv.size());
+  memcpy(b.data() + hd.off_Ac, Ac.data(), Ac.size() * 2);
+  memcpy(b.data() + hd.off_ATc, ATc.data(), ATc.size() * 2);
+  memcpy(b.data() + hd.off_Pc, Pc.data(), Pc.size() * 2);
+  memcpy(b.data() + hd.off_rowmap, rmap.data(), rmap.size() * 2);
+  memcpy(b.data() + hd.off_colmap, cmap.data(), cmap.size() * 2);
+  for (int i = 0; i < m; ++i) {
+    uint8_t f = 0;
+    if (hp.l_s[i] < -1e30 * 1e-4) f |= 1;
+    if (hp.u_s[i] > 1e30 * 1e-4) f |= 2;
+    if (hp.ctype[i] == 1) f |= 4;
+    if (hp.ctype[i] == -1) f |= 8;
+    b[hd.off_flags + i] = f;
+  }
+  memcpy(b.data() + hd.off_patch, patch.data(), patch.size() * 16);
+  CK(cudaMalloc(&h->d_tblob, hd.total));
+  CK(cudaMemcpy(h->d_tblob, b.data(), hd.total, cudaMemcpyHostToDevice));
+  const int half = ((n + 3) / 4) * 2, np2 = 2 * half;
+  for (int v = 0; v < 4; ++v) {
+    std::vector<double> vk((size_t)n * np2, 0.0);
+    const double *V = hp.V.data() + (size_t)v * n * n;
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n; ++j) vk[(size_t)k * np2 + j] = V[(size_t)j * n + k];
+    CK(cudaMalloc(&h->d_Vk[v], vk.size() * 8));
+    CK(cudaMemcpy(h->d_Vk[v], vk.data(), vk.size() * 8, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&h->d_lam, (size_t)4 * n * 8));
+  CK(cudaMemcpy(h->d_lam, hp.lam.data(), (size_t)4 * n * 8, cudaMemcpyHostToDevice));
+  h->thdr = hd;
+  const int nw = TEAM_THREADS / 32;
+  h->team_smem = (size_t)hd.total + 8 * (size_t)(5 * mp + 3 * np2 + 16 * nw + ts->ss * nct) + ((sizeof(UkfScratch) + 15) & ~15) +
+                 sizeof(LaneCtx) + 16;
+  h->team_ctas = TEAM_CTAS;
+  h->team_fn_ptr = (const void *)ts->fn;
+  CK(cudaFuncSetAttribute(h->team_fn_ptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->team_smem));
+  h->team_ok = true;
+  return MPCB_OK;
+}
+
+static void fill_team_args(mpcb_handle *h, TeamArgs &ta, int mode) {
+  const mpcb_problem &p = h->hp.p;
+  memset(&ta, 0, sizeof ta);
+  ta.hdr = h->thdr;
+  ta.blob = h->d_tblob;
+  for (int v = 0; v < 4; ++v) ta.Vk[v] = h->d_Vk[v];
+  ta.lam = h->d_lam;
+  ta.n = p.n; ta.m = p.m; ta.nX = 4 * (p.Nx + 1); ta.Nb = p.Nb; ta.uoff = 4 * (p.Nx + 1); ta.B = (int)h->B;
+  ta.sigma = p.sigma; ta.alpha = p.alpha; ta.eps_abs = p.eps_abs; ta.eps_rel = p.eps_rel; ta.eps_pinf = p.eps_prim_inf;
+  ta.adapt_tol = p.adaptive_rho_tolerance; ta.cinv = 1.0 / p.c; ta.qn_unscaled = h->qn_unscaled; ta.qn_scaled = h->qn_scaled;
+  ta.rho0 = std::min(std::max(p.rho0, MPCB_RHO_MIN), MPCB_RHO_MAX);
+  ta.check_every = p.check_termination; ta.adaptive = p.adaptive_rho; ta.adapt_interval = std::max(1, p.adaptive_rho_interval);
+  ta.max_iter = p.max_iter;
+  ta.mode = mode;
+  ta.sc = h->sc;
+  ta.xs = h->xs; ta.zs = h->zs; ta.ys = h->ys; ta.rho = h->rho; ta.u0 = h->u0;
+  ta.iter = h->iter; ta.status = h->status; ta.flip = h->flip;
+  ta.queue = h->d_queue;
+  ta.tot = h->d_tot;
+  ta.stats = h->d_stats;
+}
+
+static int launch_team(mpcb_handle *h, const TeamArgs &ta) {
+  const int grid = (int)std::min<int64_t>(h->B, (int64_t)h->num_sms * h->team_ctas);
+  CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    while (h->ev_pool.size() < 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+    e0 = h->ev_pool[0];
+    e1 = h->ev_pool[1];
+    CK(cudaEventRecord(e0, h->stream));
+  }
+  ((team_fn)h->team_fn_ptr)<<<grid, TEAM_THREADS, h->team_smem, h->stream>>>(ta);
+  CK(cudaGetLastError());
+  if (h->timing) {
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    h->ctr.admm_ms += ms;
+  }
+  h->ctr.kernel_launches += 1;
+  h->ctr.admm_launches += 1;
+  h->ctr.rounds += 1;
+  return MPCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" int mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
 extern "C" const char *mpcb_last_error(void) { return g_err.c_str(); }
@@ -337,9 +556,16 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
     return rc;
   }
   set_warps(h, h->warps);
+  rc = build_team_tables(h);
+  if (rc != MPCB_OK) {
+    mpcb_destroy(h);
+    return rc;
+  }
   CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&h->d_tot, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_tot, 16 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_tot, 0, 16 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_queue, sizeof(int)));
   CK(cudaMalloc(&h->d_stats, MPCB_NSTATS * sizeof(double)));
   CK(cudaMallocHost(&h->h_cnt, 8 * sizeof(int)));
   CK(cudaEventCreate(&h->ev_t0));
@@ -368,6 +594,10 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
     cudaFree(h->d_V[v]);
   }
   cudaFree(h->d_tot);
+  cudaFree(h->d_tblob);
+  cudaFree(h->d_lam);
+  cudaFree(h->d_queue);
+  for (int v = 0; v < 4; ++v) cudaFree(h->d_Vk[v]);
   cudaFree(h->d_stats);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -386,7 +616,7 @@ static int reset_solver_state(mpcb_handle *h) {
   CK(cudaMemsetAsync(h->ys, 0, (size_t)B * m * 8, h->stream));
   CK(cudaMemsetAsync(h->flip, 0, (size_t)B * 4, h->stream));
   CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
-  CK(cudaMemsetAsync(h->d_tot, 0, 2 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_tot, 0, 16 * sizeof(unsigned long long), h->stream));
   std::vector<double> r((size_t)B, std::min(std::max(h->hp.p.rho0, MPCB_RHO_MIN), MPCB_RHO_MAX));
   CK(cudaMemcpyAsync(h->rho, r.data(), (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -537,10 +767,17 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf)
 }
 
 static int pull_totals(mpcb_handle *h) {
-  unsigned long long t[2];
+  unsigned long long t[16];
   CK(cudaMemcpyAsync(t, h->d_tot, sizeof t, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+#ifdef TEAM_PROFILE
+  fprintf(stderr, "[team profile] Mcycles: iterations %.1f checks %.1f rebuilds %.1f post %.1f setup %.1f | team total %.1f\n",
+          t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6, t[8] / 1e6, t[9] / 1e6);
+  if (t[0]) fprintf(stderr, "[team profile] cycles per iteration, one thread: A'v %.0f | bar %.0f | S r %.0f | bar %.0f | A xt %.0f | bar %.0f\n",
+                    (double)t[10] / t[0], (double)t[11] / t[0], (double)t[12] / t[0], (double)t[13] / t[0], (double)t[14] / t[0], (double)t[15] / t[0]);
+#endif
   h->ctr.admm_iterations += (int64_t)t[0];
+  h->ctr.operator_rebuilds += (int64_t)t[2];
   CK(cudaMemsetAsync(h->d_tot, 0, sizeof t, h->stream));
   return MPCB_OK;
 }
@@ -610,14 +847,22 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
   PostArgs pa;
   fill_args(h, aa, pa, MODE_QP_ONLY);
   CK(cudaEventRecord(h->ev_t0, h->stream));
-  CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
-  pa.cnt_cur = h->cnt + 4;
-  pa.cnt_next = h->cnt;
-  pa.list_next = h->list;
   const int pgrid = (int)((B + 127) / 128);
-  qp_prepare_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_xhat);
-  h->ctr.kernel_launches += 1;
-  RC(run_rounds(h, aa, pa, 0));
+  if (h->team_ok) {
+    TeamArgs ta;
+    fill_team_args(h, ta, MODE_QP_ONLY);
+    ta.xhat = d_xhat;
+    ta.warm = 1;
+    RC(launch_team(h, ta));
+  } else {
+    CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
+    pa.cnt_cur = h->cnt + 4;
+    pa.cnt_next = h->cnt;
+    pa.list_next = h->list;
+    qp_prepare_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_xhat);
+    h->ctr.kernel_launches += 1;
+    RC(run_rounds(h, aa, pa, 0));
+  }
   if (d_u0) CK(cudaMemcpyAsync(d_u0, h->u0, (size_t)2 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
   if (d_st || d_it) {
     gather_qp_out_kernel<<<pgrid, 128, 0, h->stream>>>((int)B, h->status, h->iter, d_st, d_it);
@@ -754,17 +999,29 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   pa.n_refresh = n_refresh;
   CK(cudaEventRecord(h->ev_t0, h->stream));
   CK(cudaMemsetAsync(h->d_stats, 0, MPCB_NSTATS * sizeof(double), h->stream));
-  pa.cnt_cur = h->cnt + 4;
-  pa.cnt_next = h->cnt;
-  pa.list_next = h->list;
-  const int pgrid = (int)((B + 127) / 128);
-  init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
-  CK(cudaGetLastError());
-  h->ctr.kernel_launches += 1;
-  RC(run_rounds(h, aa, pa, 0));
-  finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
-  CK(cudaGetLastError());
-  h->ctr.kernel_launches += 1;
+  if (h->team_ok && mode == MODE_DISCRETE) {
+    TeamArgs ta;
+    fill_team_args(h, ta, MODE_DISCRETE);
+    ta.nsteps = nsteps;
+    ta.out = od;
+    ta.x0 = d_x0;
+    ta.noise_in = d_noise;
+    ta.n_refresh = n_refresh;
+    ta.warm = 0;
+    RC(launch_team(h, ta));
+  } else {
+    pa.cnt_cur = h->cnt + 4;
+    pa.cnt_next = h->cnt;
+    pa.list_next = h->list;
+    const int pgrid = (int)((B + 127) / 128);
+    init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
+    CK(cudaGetLastError());
+    h->ctr.kernel_launches += 1;
+    RC(run_rounds(h, aa, pa, 0));
+    finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
+    CK(cudaGetLastError());
+    h->ctr.kernel_launches += 1;
+  }
   CK(cudaEventRecord(h->ev_t1, h->stream));
   RC(st.back(o.i_term, od.i_term, (size_t)B, io_on_device, h->stream));
   RC(st.back(o.is_success, od.is_success, (size_t)B, io_on_device, h->stream));

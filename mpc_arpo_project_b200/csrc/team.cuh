@@ -1,0 +1,810 @@
+// Team kernel: one CTA ("team", 256 threads) owns one trajectory at a time and runs its WHOLE
+// closed loop (every control step: OSQP-equivalent ADMM solve -> controller select / clip -> plant
+// step -> UKF -> QP parameter refresh) without returning to the host.  Teams pull trajectories from
+// an atomic queue until the batch is exhausted (persistent grid, 2 CTAs per SM).
+//
+// Linear solve.  OSQP refactors its KKT matrix whenever rho changes (reference
+// src/trajectorySimulate.py:296 -> osqp_solve / adapt_rho).  Here the reduced operator
+//     S(rho) = (P + sigma I + A' diag(rho_vec) A)^-1 = V diag(1/(1+rho*lam)) V'
+// (spectral tables V, lam per sign variant, built once on the host, problem.py) is materialised
+// per trajectory IN REGISTERS: threads 2i and 2i+1 hold the two halves of row i of S (HALF doubles
+// each), so one ADMM iteration is ONE dense mat-vec with zero shared-memory traffic for the
+// matrix; r is broadcast from shared memory with 128-bit loads and the two half sums meet in a
+// shuffle.  S is rebuilt (N^3 FMAs across the team) only when the trajectory's rho adapts or its
+// velocity-sign variant flips.
+//
+// Per iteration (3 team barriers):
+//     r  = sigma*x - q + A'v        (thread pair per entry of r, ELL)      -> smem, barrier
+//     xt = S r ; x = a*xt+(1-a)*x   (thread pair per row, S in registers)  -> smem, barrier
+//     zt = A xt ; z,y update ; v = rho_vec.*z - y  (thread per row, ELL)   -> smem, barrier
+#pragma once
+#include "common.cuh"
+#include "sim.cuh"
+
+#define TEAM_THREADS 256
+#ifndef TEAM_CTAS
+#define TEAM_CTAS 2
+#endif
+
+// Optional cycle breakdown (compile with -DTEAM_PROFILE): thread 0 of every team accumulates clock64()
+// deltas per phase into tot[4..]: 4 iterations, 5 checks, 6 operator rebuilds, 7 post step, 8 lane setup, 9 total.
+#ifdef TEAM_PROFILE
+#ifndef TP_TID
+#define TP_TID 0
+#endif
+#define TP_DECL long long tp_t0 = clock64(), tp_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tp_ph = 0; const long long tp_start = tp_t0;
+#define TP_MARK(slot) { const long long tp_now = clock64(); tp_acc[slot] += tp_now - tp_t0; tp_t0 = tp_now; }
+#define TP_PH0 tp_ph = clock64();
+#define TP_PH(slot) { const long long tp_now = clock64(); tp_acc[slot] += tp_now - tp_ph; tp_ph = tp_now; }
+#define TP_FLUSH if (tid == TP_TID) { for (int q = 5; q < 11; ++q) atomicAdd(&a.tot[q + 5], (unsigned long long)tp_acc[q]); } if (tid == 0) { for (int q = 0; q < 5; ++q) atomicAdd(&a.tot[4 + q], (unsigned long long)tp_acc[q]); \
+                                 atomicAdd(&a.tot[9], (unsigned long long)(clock64() - tp_start)); }
+#else
+#define TP_DECL
+#define TP_MARK(slot)
+#define TP_PH0
+#define TP_PH(slot)
+#define TP_FLUSH
+#endif
+
+// Byte offsets into the team constant blob (global -> shared once per CTA).
+//
+// Sparse tables are ELL in "team layout".  Rows of A are handed to threads in order of decreasing
+// nnz (thread t <-> row rowmap[t]), columns of A (= rows of A') to thread PAIRS likewise
+// (pair p <-> variable colmap[p]; the pair splits the column's entries even/odd).  Every warp then
+// has its own ELL width (wA[warp], wAT2[warp]) and skips the padding of the widest rows: shared-
+// memory wavefronts, not FP64 issue, bound this kernel (profiles/team_kernel_r1.md).
+struct TeamHdr {
+  int off_q, off_D, off_Dinv, off_E, off_Einv, off_lt, off_ut;   // double vectors in natural index order
+  int off_Av;       // [WA][MP]    value e of the row thread t owns
+  int off_ATv;      // [WAT2][NCT] value pair-slot e of thread t (entry 2e + (t&1) of column colmap[t>>1])
+  int off_Pv;       // [WP][NCT/2] row colmap[p] of P
+  int off_Ac;       // [MP] uint4: 8 uint16 column indices of the thread's row
+  int off_ATc;      // [NCT] uint4: 8 uint16 row indices
+  int off_Pc;       // [WP][NCT/2] uint16
+  int off_rowmap;   // [MP] uint16
+  int off_colmap;   // [NCT/2] uint16
+  int off_flags;                                                 // uint8 per row (natural order)
+  int off_patch;                                                 // int4 {offA, offAT, which, 0} per signed entry
+  int n_patch;
+  int wA[8], wAT2[8];                                            // per-warp ELL widths
+  int total;                                                     // bytes, multiple of 16
+};
+
+struct TeamArgs {
+  TeamHdr hdr;
+  const unsigned char *blob;
+  const double *Vk[4];       // [N][NP2] k-major: Vk[k*NP2 + j] = V[j][k], zero padded
+  const double *lam;         // [4][N]
+  int n, m, nX, Nb, uoff, B;
+  double sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol, cinv, qn_unscaled, qn_scaled, rho0;
+  int check_every, adaptive, adapt_interval, max_iter;
+  int mode;                  // MODE_QP_ONLY | MODE_DISCRETE
+  int nsteps;
+  SimConst sc;
+  SimOutDev out;
+  const double *x0;          // [4][B]
+  const double *noise_in;    // [n_refresh][2][B]
+  int n_refresh;
+  // QP seam / persistent solver state
+  const double *xhat;        // [6][B] (MODE_QP_ONLY)
+  double *xs, *zs, *ys;      // [B][n], [B][m], [B][m]
+  double *rho;               // [B]
+  double *u0;                // [2][B]
+  int *iter, *status, *flip;
+  int warm;                  // 1: load x,z,y,rho from global (QP seam), 0: cold start
+  // results
+  int *queue;                // [1] next lane
+  unsigned long long *tot;   // [0] admm iterations, [1] qp solves, [2] operator rebuilds
+  double *stats;             // [MPCB_NSTATS]
+};
+
+struct LaneCtx {
+  double xtrue[4], ux[6], uP[36], xstore[4], unext[2], noise[2], xfin[4], par[7], u0[2];
+  double xintf, rho;
+  int step, iterm, succ, nsolve, variant, ukf_clamp, flip, fin, status, iter, lane;
+};
+
+struct UkfScratch {
+  double Ao[36], Bou[12], Qw[36];      // shared copies: per-thread indexed reads of kernel parameters serialise
+  double U[36], sig[78], sf[78], xm[6], Pm[36], zs[26], zp[2], S[4], Pxz[12], K[12];
+  int ok;
+};
+
+__device__ __forceinline__ int ctx_params(const SimConst &c, LaneCtx &L, const double *xe) {
+  L.par[0] = xe[0]; L.par[1] = xe[1]; L.par[2] = xe[2]; L.par[3] = xe[3];
+  L.par[4] = fabs(xe[0] - c.xr[0]) + fabs(xe[1] - c.xr[1]);
+  L.par[5] = c.is_reject ? xe[4] : 0.0;
+  L.par[6] = c.is_reject ? xe[5] : 0.0;
+  return (xe[2] >= 0 ? 0 : 1) + (xe[3] >= 0 ? 0 : 2);          // sign(0) = +1, simhelpers.py:66-67
+}
+
+// kf.predict(u); kf.update(z) (filterpy 1.4.5 as restated in oracle/ukf_ref.py, R = 0) executed by
+// ONE WARP on shared-memory operands; same operation order per output as the scalar ukf_step().
+__device__ __forceinline__ void ukf_sigma_warp(const double *x, const double *U, double *sig, int lid) {
+  for (int idx = lid; idx < 78; idx += 32) {
+    const int k = idx / 6, j = idx - 6 * k;
+    sig[idx] = (k == 0) ? x[j] : ((k <= 6) ? x[j] + U[(k - 1) * 6 + j] : x[j] - U[(k - 7) * 6 + j]);
+  }
+}
+
+__device__ __noinline__ bool ukf_step_warp(const SimConst &c, double *x, double *P, double u0, double u1, double z0, double z1,
+                                           UkfScratch &w, int lid) {
+  if (lid == 0) w.ok = chol_upper6(P, UKF_NPL, w.U) ? 1 : 0;
+  __syncwarp();
+  ukf_sigma_warp(x, w.U, w.sig, lid);
+  __syncwarp();
+  for (int idx = lid; idx < 78; idx += 32) {
+    const int k = idx / 6, i = idx - 6 * k;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc += w.Ao[i * 6 + j] * w.sig[k * 6 + j];
+    w.sf[idx] = acc + w.Bou[i * 2] * u0 + w.Bou[i * 2 + 1] * u1;
+  }
+  __syncwarp();
+  if (lid < 6) {
+    double acc = UKF_WM0 * w.sf[lid];
+    for (int k = 1; k < 13; ++k) acc += UKF_WI * w.sf[k * 6 + lid];
+    w.xm[lid] = acc;
+  }
+  __syncwarp();
+  for (int idx = lid; idx < 36; idx += 32) {
+    const int i = idx / 6, j = idx - 6 * i;
+    double acc = 0.0;
+    for (int k = 0; k < 13; ++k) acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.sf[k * 6 + i] - w.xm[i]) * (w.sf[k * 6 + j] - w.xm[j]);
+    w.Pm[idx] = acc + w.Qw[idx];
+  }
+  __syncwarp();
+  if (lid == 0) w.ok &= chol_upper6(w.Pm, UKF_NPL, w.U) ? 1 : 0;
+  __syncwarp();
+  ukf_sigma_warp(w.xm, w.U, w.sf, lid);          // filterpy 1.4.5 regenerates the points after predict
+  __syncwarp();
+  if (lid < 13) {
+    const double a = w.sf[lid * 6], b = w.sf[lid * 6 + 1];
+    w.zs[lid * 2] = sqrt(a * a + b * b);
+    w.zs[lid * 2 + 1] = atan2(b, a);
+  }
+  __syncwarp();
+  if (lid < 2) {
+    double acc = 0.0;
+    for (int k = 0; k < 13; ++k) acc += (k == 0 ? UKF_WM0 : UKF_WI) * w.zs[k * 2 + lid];
+    w.zp[lid] = acc;
+  }
+  __syncwarp();
+  if (lid < 16) {
+    double acc = 0.0;
+    if (lid < 4) {
+      const int r = lid >> 1, q = lid & 1;
+      for (int k = 0; k < 13; ++k)
+        acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.zs[k * 2 + r] - w.zp[r]) * (w.zs[k * 2 + q] - w.zp[q]);
+      w.S[lid] = acc;
+    } else {
+      const int e = lid - 4, i = e >> 1, q = e & 1;
+      for (int k = 0; k < 13; ++k)
+        acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.sf[k * 6 + i] - w.xm[i]) * (w.zs[k * 2 + q] - w.zp[q]);
+      w.Pxz[e] = acc;
+    }
+  }
+  __syncwarp();
+  const double det = w.S[0] * w.S[3] - w.S[1] * w.S[2];
+  const double SI[4] = {w.S[3] / det, -w.S[1] / det, -w.S[2] / det, w.S[0] / det};
+  if (lid < 12) {
+    const int i = lid >> 1, q = lid & 1;
+    w.K[lid] = w.Pxz[i * 2] * SI[q] + w.Pxz[i * 2 + 1] * SI[2 + q];
+  }
+  __syncwarp();
+  const double y0 = z0 - w.zp[0], y1 = z1 - w.zp[1];
+  if (lid < 6) x[lid] = w.xm[lid] + w.K[lid * 2] * y0 + w.K[lid * 2 + 1] * y1;
+  for (int idx = lid; idx < 36; idx += 32) {
+    const int i = idx / 6, j = idx - 6 * i;
+    const double ks0 = w.K[i * 2] * w.S[0] + w.K[i * 2 + 1] * w.S[2], ks1 = w.K[i * 2] * w.S[1] + w.K[i * 2 + 1] * w.S[3];
+    P[idx] = w.Pm[idx] - (ks0 * w.K[j * 2] + ks1 * w.K[j * 2 + 1]);
+  }
+  __syncwarp();
+  return w.ok != 0;
+}
+
+// The rest of one control step after the solve (trajectorySimulate.py:298-356), executed by warp 0
+// of the team on the lane context in shared memory (scalar parts by its lane 0).
+__device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfScratch &w, int lid) {
+  const SimConst &c = a.sc;
+  const size_t B = a.B;
+  const int ln = L.lane, T1 = a.out.T1, i = L.step;
+  const double up0 = L.unext[0], up1 = L.unext[1];               // ctrls[:, i], the command chosen one step ago
+  double xn[4];
+  plant_lin(c, L.xtrue, L.unext, L.noise, xn);                   // every lane of the warp: cheap, avoids a broadcast
+  __syncwarp();
+  if (lid == 0) {
+    double u[2], uraw[2];
+    int code;
+    if (L.status != 1) {                                         // failsafe LQR with integrator (:305-309)
+      const double xi = L.xintf + L.xstore[0] - c.xr[0];
+      L.xintf = xi;
+      for (int r = 0; r < 2; ++r) {
+        double acc = 0.0;
+        for (int j = 0; j < 4; ++j) acc += c.Kpf[r * 4 + j] * L.xstore[j];
+        u[r] = -acc - c.Kif[r] * xi;
+      }
+      code = 2;
+    } else {
+      L.xintf = 0.0;
+      u[0] = L.u0[0];
+      u[1] = L.u0[1];
+      code = 1;
+    }
+    uraw[0] = u[0];
+    uraw[1] = u[1];
+    const double nrm = sqrt(u[0] * u[0] + u[1] * u[1]);
+    if (nrm > c.umax0) {                                         // sequential clip (:317-319)
+      u[0] = u[0] * (c.umax0 / nrm);
+      const double nrm2 = sqrt(u[0] * u[0] + u[1] * u[1]);
+      u[1] = u[1] * (c.umax0 / nrm2);
+    }
+    L.nsolve += 1;
+    if (a.out.status) a.out.status[(size_t)i * B + ln] = (int8_t)L.status;
+    if (a.out.iters) a.out.iters[(size_t)i * B + ln] = (int16_t)L.iter;
+    if (a.out.ctrlr_seq) a.out.ctrlr_seq[(size_t)i * B + ln] = (uint8_t)code;
+    if (a.out.u_raw) {
+      a.out.u_raw[((size_t)0 * (T1 - 1) + i) * B + ln] = uraw[0];
+      a.out.u_raw[((size_t)1 * (T1 - 1) + i) * B + ln] = uraw[1];
+    }
+    if (a.out.ctrl) {
+      a.out.ctrl[((size_t)0 * T1 + i + 1) * B + ln] = u[0];
+      a.out.ctrl[((size_t)1 * T1 + i + 1) * B + ln] = u[1];
+    }
+    L.unext[0] = u[0];
+    L.unext[1] = u[1];
+    if (i >= 1 && success_cond(c, L.xtrue)) L.succ = 1;          // scan over x_true[:, 1 .. i_term-1] (:369-376)
+    for (int k = 0; k < 4; ++k) L.xfin[k] = L.xtrue[k];
+  }
+  __syncwarp();
+  double xe[6];
+  if (c.has_noise) {
+    const double z0 = sqrt(xn[0] * xn[0] + xn[1] * xn[1]), z1 = atan2(xn[1], xn[0]);
+    const bool ok = ukf_step_warp(c, L.ux, L.uP, up0, up1, z0, z1, w, lid);
+    if (!ok && lid == 0) L.ukf_clamp = 1;
+    for (int k = 0; k < 6; ++k) xe[k] = L.ux[k];
+  } else {
+    for (int k = 0; k < 4; ++k) xe[k] = xn[k];
+    xe[4] = xe[5] = 0.0;
+  }
+  __syncwarp();
+  if (lid == 0) {
+    L.variant = ctx_params(c, L, xe);
+    if (c.in_track) {                                            // in-place x/y swap of the stored estimate, simhelpers.py:72
+      const double t = xe[0];
+      xe[0] = xe[1];
+      xe[1] = t;
+    }
+    for (int k = 0; k < 4; ++k) L.xstore[k] = xe[k];
+    if (a.out.x_est)
+      for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1 + i + 1) * B + ln] = xe[k];
+    if (a.out.x_true)
+      for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1 + i + 1) * B + ln] = xn[k];
+    for (int k = 0; k < 4; ++k) L.xtrue[k] = xn[k];
+    if (c.has_noise && ((i + 1) % c.noise_length == 0)) {
+      const int r = min((i + 1) / c.noise_length, a.n_refresh - 1);
+      L.noise[0] = a.noise_in[((size_t)r * 2 + 0) * B + ln];
+      L.noise[1] = a.noise_in[((size_t)r * 2 + 1) * B + ln];
+    }
+    L.step = i + 1;
+    if (i + 1 >= a.nsteps) {
+      L.fin = 1;                                                 // i_term stays nsim
+    } else if (terminated(c, xn)) {
+      L.iterm = i + 1;
+      L.fin = 1;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ void lane_init(const TeamArgs &a, LaneCtx &L, int ln) {
+  const SimConst &c = a.sc;
+  const size_t B = a.B;
+  L.lane = ln;
+  L.rho = a.rho0;
+  L.xintf = 0.0;
+  L.step = 0; L.succ = 0; L.nsolve = 0; L.ukf_clamp = 0; L.flip = 0; L.fin = 0; L.status = -10; L.iter = 0;
+  L.u0[0] = L.u0[1] = 0.0;
+  if (a.mode == MODE_QP_ONLY) {
+    double xe[6];
+    for (int k = 0; k < 6; ++k) xe[k] = a.xhat[k * B + ln];
+    L.variant = ctx_params(c, L, xe);
+    if (a.warm) L.rho = a.rho[ln];
+    L.iterm = 0;
+    return;
+  }
+  double x[6];
+  for (int k = 0; k < 4; ++k) x[k] = a.x0[k * B + ln];
+  x[4] = x[5] = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    L.xtrue[k] = x[k];
+    L.xstore[k] = x[k];
+    L.xfin[k] = nan("");
+  }
+  for (int k = 0; k < 6; ++k) L.ux[k] = x[k];
+  for (int k = 0; k < 36; ++k) L.uP[k] = (k % 7 == 0) ? ((k / 7 < 4) ? 1e-20 : 1.0) : 0.0;
+  L.unext[0] = L.unext[1] = 0.0;
+  L.noise[0] = (c.has_noise && a.noise_in) ? a.noise_in[ln] : 0.0;
+  L.noise[1] = (c.has_noise && a.noise_in) ? a.noise_in[B + ln] : 0.0;
+  L.variant = ctx_params(c, L, x);
+  const int T1 = a.out.T1;
+  if (a.out.x_true) for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1) * B + ln] = x[k];
+  if (a.out.x_est) for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1) * B + ln] = x[k];
+  if (a.out.ctrl) for (int k = 0; k < 2; ++k) a.out.ctrl[((size_t)k * T1) * B + ln] = 0.0;
+  L.iterm = a.nsteps;
+  if (a.nsteps <= 0) L.fin = 1;
+  else if (terminated(c, x)) { L.iterm = 0; L.fin = 1; }
+}
+
+__device__ __noinline__ void lane_finalize(const TeamArgs &a, LaneCtx &L) {
+  const int ln = L.lane;
+  if (a.mode == MODE_QP_ONLY) {
+    a.status[ln] = L.status;
+    a.iter[ln] = L.iter;
+    a.u0[ln] = L.u0[0];
+    a.u0[(size_t)a.B + ln] = L.u0[1];
+    a.rho[ln] = L.rho;
+    if (L.flip) a.flip[ln] = 1;
+    atomicAdd(&a.tot[1], 1ull);
+    return;
+  }
+  double d2 = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const double d = L.xfin[k] - a.sc.xr[k];
+    d2 += d * d;
+  }
+  const double fd = sqrt(d2);
+  if (a.out.i_term) a.out.i_term[ln] = L.iterm;
+  if (a.out.is_success) a.out.is_success[ln] = L.succ;
+  if (a.out.final_dist) a.out.final_dist[ln] = fd;
+  if (a.out.ukf_clamped) a.out.ukf_clamped[ln] = L.ukf_clamp;
+  a.rho[ln] = L.rho;
+  const double f = (fd == fd) ? fd : 0.0;
+  atomicAdd(&a.stats[0], f);
+  atomicAdd(&a.stats[1], f * f);
+  if (L.succ) atomicAdd(&a.stats[2], 1.0);
+  atomicAdd(&a.stats[3], 1.0);
+  atomicAdd(&a.stats[4], (double)L.iterm);
+  atomicAdd(&a.stats[5], (double)L.nsolve);
+  if (L.flip) atomicAdd(&a.stats[7], 1.0);
+  if (L.ukf_clamp) atomicAdd(&a.stats[8], 1.0);
+  if (L.iterm < a.nsteps) atomicAdd(&a.stats[9], 1.0);
+  atomicAdd(&a.tot[1], (unsigned long long)L.nsolve);
+}
+
+// W entries of one ELL row: values at vals[e*stride], 16-bit column indices packed in c.
+template <int W>
+__device__ __forceinline__ double ell_dot(const double *vals, int stride, const uint4 &c, const double *vec) {
+  const unsigned cw[4] = {c.x, c.y, c.z, c.w};
+  double v[W], g[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    v[e] = vals[e * stride];
+    g[e] = vec[(e & 1) ? (cw[e >> 1] >> 16) : (cw[e >> 1] & 0xffffu)];
+  }
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    if (e & 1) acc1 = fma(v[e], g[e], acc1);
+    else acc0 = fma(v[e], g[e], acc0);
+  }
+  return acc0 + acc1;
+}
+
+// ------------------------------------------------------------------------------------------
+// N variables, M rows (M <= 256, 2N <= 256); WA (<= 8), WAT2 (<= 8, entry PAIRS), WP are the maximum
+// ELL widths the instantiation supports.  Of the HALF entries of S a thread owns, the last SS live in
+// shared memory ([SS][NCT], conflict-free) and the rest in registers.
+template <int N, int M, int WA, int WAT2, int WP, int SS>
+__global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __grid_constant__ TeamArgs a) {
+  constexpr int TEAM = TEAM_THREADS;
+  constexpr int HALF = ((N + 3) / 4) * 2;  // entries of a row of S per thread (even); 2*HALF >= N
+  constexpr int NP2 = 2 * HALF;            // padded n-vector length in shared memory / Vk row length
+  constexpr int MP = (M + 1) & ~1;
+  constexpr int NW = TEAM / 32;
+  constexpr int NCT = ((2 * N + 31) / 32) * 32;   // threads that run the pair phases: whole warps (shuffles stay convergent)
+  constexpr int SR = HALF - SS;            // entries of S per thread kept in registers
+  static_assert(SS % 2 == 0 && SR % 2 == 0 && SR > 0, "S split must be even");
+  static_assert(2 * N <= TEAM && M <= TEAM && WA <= 8 && WAT2 <= 8, "team too small");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TeamHdr &h = a.hdr;
+  const int tid = threadIdx.x, warp = tid >> 5, lid = tid & 31;
+
+  // ---- shared memory carve-up: [blob | vbuf MP | rbuf NP2 | xtbuf NP2 | dk NP2 | red 16*NW | lo hi rinv dy MP each | Ssm SS*NCT | ukf | ctx]
+  double *vbuf = reinterpret_cast<double *>(smem + h.total);
+  double *rbuf = vbuf + MP;
+  double *xtbuf = rbuf + NP2;
+  double *dk = xtbuf + NP2;
+  double *red = dk + NP2;
+  double *lobuf = red + 16 * NW;
+  double *hibuf = lobuf + MP;
+  double *rinvbuf = hibuf + MP;
+  double *dybuf = rinvbuf + MP;
+  double *Ssm = dybuf + MP;
+  UkfScratch &ukf = *reinterpret_cast<UkfScratch *>(Ssm + SS * NCT);
+  LaneCtx &L = *reinterpret_cast<LaneCtx *>(reinterpret_cast<unsigned char *>(&ukf) + ((sizeof(UkfScratch) + 15) & ~15));
+  __shared__ int s_lane;
+
+  for (int o = tid * 16; o < h.total; o += TEAM * 16)
+    *reinterpret_cast<int4 *>(smem + o) = *reinterpret_cast<const int4 *>(a.blob + o);
+  if (tid < NP2 - N) { rbuf[N + tid] = 0.0; xtbuf[N + tid] = 0.0; dk[N + tid] = 0.0; }
+  if (tid < 36) { ukf.Ao[tid] = a.sc.Ao[tid]; ukf.Qw[tid] = a.sc.Qw[tid]; }
+  if (tid < 12) ukf.Bou[tid] = a.sc.Bou[tid];
+  for (int o = tid; o < SS * NCT; o += TEAM) Ssm[o] = 0.0;
+  __syncthreads();
+
+  const double *qv = reinterpret_cast<const double *>(smem + h.off_q);
+  const double *Dv = reinterpret_cast<const double *>(smem + h.off_D);
+  const double *Dinv = reinterpret_cast<const double *>(smem + h.off_Dinv);
+  const double *Ev = reinterpret_cast<const double *>(smem + h.off_E);
+  const double *Einv = reinterpret_cast<const double *>(smem + h.off_Einv);
+  const double *lt = reinterpret_cast<const double *>(smem + h.off_lt);
+  const double *ut = reinterpret_cast<const double *>(smem + h.off_ut);
+  double *Avals = reinterpret_cast<double *>(smem + h.off_Av);
+  double *ATvals = reinterpret_cast<double *>(smem + h.off_ATv);
+  const double *Pvals = reinterpret_cast<const double *>(smem + h.off_Pv);
+  const uint4 *Acols = reinterpret_cast<const uint4 *>(smem + h.off_Ac);
+  const uint4 *ATcols = reinterpret_cast<const uint4 *>(smem + h.off_ATc);
+  const uint16_t *Pcols = reinterpret_cast<const uint16_t *>(smem + h.off_Pc);
+  const uint8_t *flags = reinterpret_cast<const uint8_t *>(smem + h.off_flags);
+  const int4 *patch = reinterpret_cast<const int4 *>(smem + h.off_patch);
+
+  // roles: thread pair (2p, 2p+1) <-> variable col = colmap[p] / row col of S; thread t <-> row rowmap[t] of A
+  const int pairi = tid >> 1, half = tid & 1;
+  const bool has_col = pairi < N;        // pair member
+  const bool col_warp = tid < NCT;       // warp-uniform: executes the pair phases (S = 0 for pairs beyond N)
+  const bool has_row = tid < M;
+  const int col = has_col ? reinterpret_cast<const uint16_t *>(smem + h.off_colmap)[pairi] : 0;
+  const int row = has_row ? reinterpret_cast<const uint16_t *>(smem + h.off_rowmap)[tid] : 0;
+  const int wA = h.wA[warp], wAT2 = h.wAT2[warp];          // warp-uniform ELL widths
+  const double sigma = a.sigma, alpha = a.alpha, oma = 1.0 - a.alpha;
+
+  // A warp-uniform switch picks a fully unrolled body, so every load of a phase is in flight at once.
+  auto applyA = [&](const double *vec) -> double {          // row `row` of A times vec (thread tid < M)
+    const uint4 c = Acols[tid];
+    const double *v = Avals + tid;
+    switch (wA) {
+      case 1: return ell_dot<1>(v, MP, c, vec);
+      case 2: return ell_dot<2>(v, MP, c, vec);
+      case 3: return ell_dot<3>(v, MP, c, vec);
+      case 4: return ell_dot<4>(v, MP, c, vec);
+      case 5: return ell_dot<5>(v, MP, c, vec);
+      case 6: return ell_dot<6>(v, MP, c, vec);
+      case 7: return ell_dot<7>(v, MP, c, vec);
+      case 8: return ell_dot<8>(v, MP, c, vec);
+      default: return 0.0;
+    }
+  };
+  auto applyAT = [&](const double *vec) -> double {         // (A' vec)[col], pair-summed (threads < NCT)
+    const uint4 c = ATcols[tid];
+    const double *v = ATvals + tid;
+    double acc;
+    switch (wAT2) {
+      case 1: acc = ell_dot<1>(v, NCT, c, vec); break;
+      case 2: acc = ell_dot<2>(v, NCT, c, vec); break;
+      case 3: acc = ell_dot<3>(v, NCT, c, vec); break;
+      case 4: acc = ell_dot<4>(v, NCT, c, vec); break;
+      case 5: acc = ell_dot<5>(v, NCT, c, vec); break;
+      case 6: acc = ell_dot<6>(v, NCT, c, vec); break;
+      case 7: acc = ell_dot<7>(v, NCT, c, vec); break;
+      case 8: acc = ell_dot<8>(v, NCT, c, vec); break;
+      default: acc = 0.0; break;
+    }
+    return acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+  };
+  auto applyP = [&](const double *vec) -> double {          // row col of P times vec (both pair members)
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < WP; ++e) acc = fma(Pvals[e * (NCT / 2) + pairi], vec[Pcols[e * (NCT / 2) + pairi]], acc);
+    return acc;
+  };
+  auto team_max = [&](auto &vals) {                  // vals: double[CNT], CNT <= 12, stays in registers
+    constexpr int CNT = sizeof(vals) / sizeof(double);
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) vals[q] = warp_max(vals[q]);
+    __syncthreads();
+    if (lid == 0) {
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) red[warp * 16 + q] = vals[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) {
+      double v = red[q];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) v = fmax(v, red[w * 16 + q]);
+      vals[q] = v;
+    }
+  };
+
+  double S[SR];                          // S[col][half*HALF .. half*HALF+SR); the next SS entries are in Ssm[.][tid]
+  int op_variant = 0;                    // sign variant baked into Avals / ATvals (blob = variant 0)
+  unsigned long long my_iters = 0, my_rebuilds = 0;
+  TP_DECL
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_lane = atomicAdd(a.queue, 1);
+    __syncthreads();
+    const int ln = s_lane;
+    if (ln >= a.B) break;
+    if (tid == 0) lane_init(a, L, ln);
+    // solver iterates: x[col] (both pair members), z[row] / y[row]
+    double x = 0.0, z = 0.0, y = 0.0;
+    if (a.warm) {
+      if (has_col) x = a.xs[(size_t)ln * N + col];
+      if (has_row) {
+        z = a.zs[(size_t)ln * M + row];
+        y = a.ys[(size_t)ln * M + row];
+      }
+    }
+    double op_rho = -1.0;                // rho the registers' S was built for (new lane: force a rebuild)
+    __syncthreads();
+    TP_MARK(4)
+
+    // =============================== control steps ===============================
+    while (!L.fin) {
+      const int variant = L.variant;
+      double rho = L.rho;
+      if (has_row) {
+        double lo = lt[row], hi = ut[row];
+        if (row < 4) lo = hi = -L.par[row] * Ev[row];
+        else if (row >= M - 2) lo = hi = L.par[5 + (row - (M - 2))] * Ev[row];
+        else if (row >= a.nX && row < a.nX + 5 * (a.Nb + 1) && (row - a.nX) % 5 == 3) {
+          hi = L.par[4] * Ev[row];
+          if (hi - lo < MPCB_RHO_TOL) L.flip = 1;      // benign race: every writer stores 1
+        }
+        lobuf[tid] = lo;                               // own slot only: no barrier needed before own reads
+        hibuf[tid] = hi;
+      }
+      if (variant != op_variant) {       // re-sign the (Nx+1) velocity rows of A and A'
+        for (int p = tid; p < h.n_patch; p += TEAM) {
+          const int4 e = patch[p];
+          const bool neg_new = (e.z == 1) ? (variant & 1) : ((variant & 2) != 0);
+          const bool neg_old = (e.z == 1) ? (op_variant & 1) : ((op_variant & 2) != 0);
+          if (neg_new != neg_old) {
+            Avals[e.x] = -Avals[e.x];
+            ATvals[e.y] = -ATvals[e.y];
+          }
+        }
+      }
+      int iter = 0, st = -10;
+      bool need_op = (variant != op_variant) || (rho != op_rho);
+      op_variant = variant;
+      const uint8_t fl = has_row ? flags[row] : (uint8_t)8;
+      __syncthreads();
+
+      // =============================== one solve ===============================
+      while (st == -10) {
+        if (need_op) {                   // S = V diag(1/(1+rho*lam)) V'
+          if (tid < N) dk[tid] = 1.0 / (1.0 + rho * a.lam[variant * N + tid]);
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < SR; ++j) S[j] = 0.0;
+          if (has_col) {
+            const double *Vk = a.Vk[variant];
+            double T[SS > 0 ? SS : 1];
+#pragma unroll
+            for (int j = 0; j < SS; ++j) T[j] = 0.0;
+            for (int k = 0; k < N; ++k) {
+              const double *vrow = Vk + (size_t)k * NP2;
+              const double tk = __ldg(vrow + col) * dk[k];
+              const double2 *r2 = reinterpret_cast<const double2 *>(vrow + half * HALF);
+#pragma unroll
+              for (int j = 0; j < SR / 2; ++j) {
+                const double2 vv = __ldg(r2 + j);
+                S[2 * j] = fma(tk, vv.x, S[2 * j]);
+                S[2 * j + 1] = fma(tk, vv.y, S[2 * j + 1]);
+              }
+#pragma unroll
+              for (int j = 0; j < SS / 2; ++j) {
+                const double2 vv = __ldg(r2 + SR / 2 + j);
+                T[2 * j] = fma(tk, vv.x, T[2 * j]);
+                T[2 * j + 1] = fma(tk, vv.y, T[2 * j + 1]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < SS; ++j) Ssm[j * NCT + tid] = T[j];
+          }
+          op_rho = rho;
+          need_op = false;
+          ++my_rebuilds;
+          TP_MARK(2)
+        }
+        const double rv = (fl & 8) ? MPCB_RHO_MIN : ((fl & 4) ? MPCB_RHO_EQ * rho : rho);
+        if (has_row) {
+          rinvbuf[tid] = 1.0 / rv;
+          vbuf[row] = rv * z - y;
+        }
+        __syncthreads();
+        // ---- check_every ADMM iterations
+        const int last_it = a.check_every - 1;
+        for (int it = 0; it <= last_it; ++it) {
+          TP_PH0
+          if (col_warp) {
+            const double s = applyAT(vbuf);
+            if (has_col && half == 0) rbuf[col] = sigma * x - qv[col] + s;
+          }
+          TP_PH(5)
+          __syncthreads();
+          TP_PH(6)
+          if (col_warp) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
+#pragma unroll
+            for (int j = 0; j < SS / 2; ++j) {          // shared-memory part first: its loads have the longest chain
+              const double2 rr = r2[SR / 2 + j];
+              const double s0 = Ssm[(2 * j) * NCT + tid], s1 = Ssm[(2 * j + 1) * NCT + tid];
+              if (j & 1) {
+                a2 = fma(s0, rr.x, a2);
+                a3 = fma(s1, rr.y, a3);
+              } else {
+                a0 = fma(s0, rr.x, a0);
+                a1 = fma(s1, rr.y, a1);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < SR / 2; ++j) {
+              const double2 rr = r2[j];
+              if (j & 1) {
+                a2 = fma(S[2 * j], rr.x, a2);
+                a3 = fma(S[2 * j + 1], rr.y, a3);
+              } else {
+                a0 = fma(S[2 * j], rr.x, a0);
+                a1 = fma(S[2 * j + 1], rr.y, a1);
+              }
+            }
+            double xt = (a0 + a1) + (a2 + a3);
+            xt += __shfl_xor_sync(0xffffffffu, xt, 1);
+            if (has_col && half == 0) xtbuf[col] = xt;
+            x = alpha * xt + oma * x;
+          }
+          TP_PH(7)
+          __syncthreads();
+          TP_PH(8)
+          if (has_row) {
+            const double zt = applyA(xtbuf);
+            const double zr = alpha * zt + oma * z;
+            const double zn = fmin(fmax(zr + rinvbuf[tid] * y, lobuf[tid]), hibuf[tid]);
+            const double dy = rv * (zr - zn);
+            y += dy;
+            z = zn;
+            vbuf[row] = rv * zn - y;
+            if (it == last_it) dybuf[tid] = dy;        // only the block's last delta_y feeds the infeasibility test
+          }
+          TP_PH(9)
+          __syncthreads();
+          TP_PH(10)
+        }
+        iter += a.check_every;
+        my_iters += (unsigned long long)a.check_every;
+        TP_MARK(0)
+
+        // ---- update_info (OSQP auxil.c): unscaled residuals decide termination; the scaled ones are
+        //      only needed when rho may adapt, so they are reduced lazily
+        if (has_col && half == 0) xtbuf[col] = x;
+        if (has_row) vbuf[row] = y;
+        __syncthreads();
+        double Ax = 0.0, Px = 0.0, dv = 0.0;
+        double mu[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) mu[q] = 0.0;
+        if (has_row) {
+          Ax = applyA(xtbuf);
+          const double ei = Einv[row];
+          mu[0] = fabs(ei * (Ax - z));
+          mu[1] = fabs(ei * z);
+          mu[2] = fabs(ei * Ax);
+        }
+        const double Aty = col_warp ? applyAT(vbuf) : 0.0;
+        if (has_col) {
+          Px = applyP(xtbuf);
+          dv = qv[col] + Px + Aty;
+          const double di = Dinv[col];
+          mu[3] = fabs(di * dv);
+          mu[4] = fabs(di * Px);
+          mu[5] = fabs(di * Aty);
+        }
+        team_max(mu);
+        const double pri_u = mu[0], nz_u = mu[1], nax_u = mu[2], dua_u = mu[3] * a.cinv, npx_u = mu[4], naty_u = mu[5];
+
+        // ---- check_termination; the primal-infeasibility certificate is built once if needed (uniform branch)
+        bool cert_ready = false;
+        double ndy = 0, lhs = 0, natdy = 0;
+        auto check = [&](double k) -> int {
+          const double eps_p = k * a.eps_abs + k * a.eps_rel * fmax(nz_u, nax_u);
+          const double eps_d = k * a.eps_abs + k * a.eps_rel * a.cinv * fmax(a.qn_unscaled, fmax(naty_u, npx_u));
+          const bool prim_ok = pri_u < eps_p, dual_ok = dua_u < eps_d;
+          if (prim_ok && dual_ok) return (k > 1.0) ? 2 : 1;
+          if (!prim_ok) {
+            if (!cert_ready) {
+              double n1 = 0, l1 = 0;
+              __syncthreads();
+              if (has_row) {
+                double d = dybuf[tid];
+                if ((fl & 3) == 3) d = 0.0;
+                else if (fl & 2) d = fmin(d, 0.0);
+                else if (fl & 1) d = fmax(d, 0.0);
+                vbuf[row] = d;
+                n1 = fabs(Ev[row] * d);
+                l1 = hibuf[tid] * fmax(d, 0.0) + lobuf[tid] * fmin(d, 0.0);
+              }
+              l1 = warp_sum(l1);
+              __syncthreads();
+              if (lid == 0) red[warp * 16 + 15] = l1;
+              const double atdy = col_warp ? applyAT(vbuf) : 0.0;
+              const double n2 = has_col ? fabs(Dinv[col] * atdy) : 0.0;
+              double two[2] = {n1, n2};
+              team_max(two);
+              ndy = two[0];
+              natdy = two[1];
+              lhs = 0.0;
+#pragma unroll
+              for (int w = 0; w < NW; ++w) lhs += red[w * 16 + 15];
+              cert_ready = true;
+            }
+            const double eps_i = k * a.eps_pinf;
+            if (ndy > MPCB_DIV_TOL && lhs < -eps_i * ndy && natdy < eps_i * ndy) return (k > 1.0) ? 3 : -3;
+          }
+          return -10;
+        };
+        st = check(1.0);
+        if (st == -10) {
+          if (a.adaptive && (iter % a.adapt_interval == 0)) {   // compute_rho_estimate on the SCALED residuals (OSQP 0.6.x)
+            double ms[6];
+            ms[0] = has_row ? fabs(Ax - z) : 0.0;
+            ms[1] = has_row ? fabs(z) : 0.0;
+            ms[2] = has_row ? fabs(Ax) : 0.0;
+            ms[3] = has_col ? fabs(dv) : 0.0;
+            ms[4] = has_col ? fabs(Px) : 0.0;
+            ms[5] = has_col ? fabs(Aty) : 0.0;
+            team_max(ms);
+            const double pr = ms[0] / (fmax(ms[1], ms[2]) + 1e-10);
+            const double du = ms[3] / (fmax(a.qn_scaled, fmax(ms[5], ms[4])) + 1e-10);
+            double est = rho * sqrt(pr / (du + 1e-10));
+            est = fmin(fmax(est, MPCB_RHO_MIN), MPCB_RHO_MAX);
+            if (est > rho * a.adapt_tol || est < rho / a.adapt_tol) {
+              rho = est;
+              need_op = true;
+            }
+          }
+          if (iter >= a.max_iter) {
+            st = check(10.0);
+            if (st == -10) st = -2;
+          }
+        }
+        __syncthreads();                 // red / vbuf reads of this check are done before the next block writes
+        TP_MARK(1)
+      }  // solve
+
+      // ---- hand the result to the lane context, run the rest of the control step on warp 0
+      if (tid == 0) {
+        L.rho = rho;
+        L.status = st;
+        L.iter = iter;
+        L.u0[0] = Dv[a.uoff] * xtbuf[a.uoff];
+        L.u0[1] = Dv[a.uoff + 1] * xtbuf[a.uoff + 1];
+        if (a.mode == MODE_QP_ONLY) L.fin = 1;
+      }
+      if (warp == 0 && a.mode != MODE_QP_ONLY) {
+        __syncwarp();
+        lane_post_step(a, L, ukf, lid);
+      }
+      __syncthreads();
+      TP_MARK(3)
+    }  // control steps
+
+    // ---- lane done: persist solver iterates (QP seam warm start / mpcb_qp_get_state), final results
+    if (has_col && half == 0) a.xs[(size_t)ln * N + col] = x;
+    if (has_row) {
+      a.zs[(size_t)ln * M + row] = z;
+      a.ys[(size_t)ln * M + row] = y;
+    }
+    if (tid == 0) lane_finalize(a, L);
+  }
+  TP_FLUSH
+  if (tid == 0) {
+    if (my_iters) atomicAdd(&a.tot[0], my_iters);
+    if (my_rebuilds) atomicAdd(&a.tot[2], my_rebuilds);
+  }
+}
