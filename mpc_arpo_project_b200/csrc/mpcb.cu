@@ -63,7 +63,13 @@ struct HostProblem {
   std::vector<int32_t> ctype;
 };
 
+struct StageBuf {
+  void *ptr = nullptr;
+  size_t cap = 0;
+};
+
 struct mpcb_handle {
+  std::vector<StageBuf> stage_pool;   // cached device staging buffers for host-pointer calls
   int device = 0;
   cudaStream_t stream = nullptr;
   HostProblem hp;
@@ -594,6 +600,7 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
     cudaFree(h->d_V[v]);
   }
   cudaFree(h->d_tot);
+  for (StageBuf &b : h->stage_pool) cudaFree(b.ptr);
   cudaFree(h->d_tblob);
   cudaFree(h->d_lam);
   cudaFree(h->d_queue);
@@ -782,19 +789,32 @@ static int pull_totals(mpcb_handle *h) {
   return MPCB_OK;
 }
 
-// Staging of host <-> device batch arrays
+// Staging of host <-> device batch arrays.  Device staging buffers are cached in the handle (grow-only,
+// matched by request order), so repeated host-pointer calls do not pay cudaMalloc / cudaFree.
 struct Stage {
-  std::vector<void *> owned;
-  ~Stage() {
-    for (void *p : owned) cudaFree(p);
+  std::vector<StageBuf> *pool;
+  size_t next = 0;
+  explicit Stage(std::vector<StageBuf> *p) : pool(p) {}
+  int grab(size_t bytes, void **out) {
+    if (next == pool->size()) pool->push_back(StageBuf());
+    StageBuf &b = (*pool)[next++];
+    if (b.cap < bytes) {
+      if (b.ptr) CK(cudaFree(b.ptr));
+      b.ptr = nullptr;
+      b.cap = 0;
+      CK(cudaMalloc(&b.ptr, bytes));
+      b.cap = bytes;
+    }
+    *out = b.ptr;
+    return MPCB_OK;
   }
   template <typename T>
   int in(const T *src, size_t count, int on_device, cudaStream_t s, const T **out) {
     if (!src) { *out = nullptr; return MPCB_OK; }
     if (on_device) { *out = src; return MPCB_OK; }
     void *d = nullptr;
-    CK(cudaMalloc(&d, count * sizeof(T)));
-    owned.push_back(d);
+    int rc = grab(count * sizeof(T), &d);
+    if (rc != MPCB_OK) return rc;
     CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     *out = (const T *)d;
     return MPCB_OK;
@@ -804,8 +824,8 @@ struct Stage {
     if (!dst) { *dev = nullptr; return MPCB_OK; }
     if (on_device) { *dev = dst; return MPCB_OK; }
     void *d = nullptr;
-    CK(cudaMalloc(&d, count * sizeof(T)));
-    owned.push_back(d);
+    int rc = grab(count * sizeof(T), &d);
+    if (rc != MPCB_OK) return rc;
     *dev = (T *)d;
     return MPCB_OK;
   }
@@ -835,7 +855,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
   if (!h || !xhat) return fail(MPCB_ERR_INVALID, "null argument");
   if (h->B == 0 || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_batch_alloc(B) must precede mpcb_qp_solve with the same B");
   CK(cudaSetDevice(h->device));
-  Stage st;
+  Stage st(&h->stage_pool);
   const double *d_xhat;
   double *d_u0;
   int32_t *d_st, *d_it;
@@ -897,7 +917,7 @@ extern "C" int mpcb_ukf_step(mpcb_handle *h, int64_t B, double *x, double *P, co
                              int io_on_device) {
   if (!h || !x || !P || !u || !z || B < 1) return fail(MPCB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  Stage st;
+  Stage st(&h->stage_pool);
   const double *dxi, *dPi, *du, *dz;
   RC(st.in((const double *)x, (size_t)6 * B, io_on_device, h->stream, &dxi));
   RC(st.in((const double *)P, (size_t)36 * B, io_on_device, h->stream, &dPi));
@@ -915,7 +935,7 @@ extern "C" int mpcb_ukf_step(mpcb_handle *h, int64_t B, double *x, double *P, co
 extern "C" int mpcb_plant_lin_step(mpcb_handle *h, int64_t B, double *x, const double *u, const double *w, int io_on_device) {
   if (!h || !x || !u || B < 1) return fail(MPCB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
-  Stage st;
+  Stage st(&h->stage_pool);
   const double *dx, *du, *dw;
   RC(st.in((const double *)x, (size_t)4 * B, io_on_device, h->stream, &dx));
   RC(st.in(u, (size_t)2 * B, io_on_device, h->stream, &du));
@@ -932,7 +952,7 @@ extern "C" int mpcb_plant_rk4(mpcb_handle *h, int64_t B, double *x, const double
                               int io_on_device) {
   if (!h || !x || !u || B < 1 || nsub < 0) return fail(MPCB_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(h->device));
-  Stage st;
+  Stage st(&h->stage_pool);
   const double *dx, *du, *dw;
   RC(st.in((const double *)x, (size_t)4 * B, io_on_device, h->stream, &dx));
   RC(st.in(u, (size_t)2 * B, io_on_device, h->stream, &du));
@@ -958,7 +978,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   static const mpcb_sim_out none = {};
   const mpcb_sim_out &o = out ? *out : none;
   const size_t T1 = (size_t)nsteps + 1;
-  Stage st;
+  Stage st(&h->stage_pool);
   const double *d_x0, *d_noise;
   RC(st.in(x0, (size_t)4 * B, io_on_device, h->stream, &d_x0));
   RC(st.in(noise, noise ? (size_t)n_refresh * 2 * B : 0, io_on_device, h->stream, &d_noise));

@@ -28,9 +28,10 @@ def _is_torch(a) -> bool:
 class _Arrays:
     """Allocates outputs of the same kind (numpy / torch-cuda) as the inputs and hands out pointers."""
 
-    def __init__(self, like, device_index: int):
+    def __init__(self, like, device_index: int, host_cache=None):
         self.on_device = _is_torch(like) and like.is_cuda
         self.dev = device_index
+        self.host_cache = host_cache        # dict of pinned host arrays reused across calls, or None
         if _is_torch(like) and not like.is_cuda:
             raise TypeError("torch inputs must be CUDA tensors (use numpy for host arrays)")
         self._keep = []
@@ -57,7 +58,17 @@ class _Arrays:
         self._keep.append(a)
         return C.c_void_p(a.ctypes.data)
 
-    def new(self, shape, dtype=np.float64):
+    def new(self, shape, dtype=np.float64, name=None):
+        if not self.on_device and self.host_cache is not None and name is not None:
+            key = (name, tuple(shape), np.dtype(dtype).str)
+            a = self.host_cache.get(key)
+            if a is None:
+                import torch
+                tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8, np.int8: torch.int8,
+                       np.int16: torch.int16}[dtype]
+                a = torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
+                self.host_cache[key] = a
+            return a, C.c_void_p(a.ctypes.data)
         if self.on_device:
             import torch
             tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8, np.int8: torch.int8,
@@ -69,7 +80,11 @@ class _Arrays:
 
 
 class Engine:
-    def __init__(self, problem: Problem, device: int = 0):
+    """``pin_outputs=True`` returns host results in page-locked arrays that the engine keeps and
+    OVERWRITES on the next call with the same shapes (fast D2H for repeated batches; copy what you keep)."""
+
+    def __init__(self, problem: Problem, device: int = 0, pin_outputs: bool = False):
+        self._host_cache = {} if pin_outputs else None
         self.lib = _lib.load()
         self.problem = problem
         self.device = int(device)
@@ -203,7 +218,7 @@ class Engine:
         }
         for name in ("i_term", "is_success", "final_dist", "ukf_clamped") + tuple(record):
             shape, dt = spec[name]
-            arr, p = ar.new(shape, dt)
+            arr, p = ar.new(shape, dt, name)
             res[name] = arr
             setattr(out, name, p)
         return out, res
@@ -225,7 +240,7 @@ class Engine:
         B = x0.shape[1]
         if B != self.B:
             self.batch_alloc(B)
-        ar = _Arrays(x0, self.device)
+        ar = _Arrays(x0, self.device, self._host_cache)
         out, res = self._sim_outputs(ar, B, nsteps + 1, record)
         R = 0 if noise is None else noise.shape[0]
         _lib.check(self.lib.mpcb_simulate_discrete(self._h, B, int(nsteps), ar.ptr(x0, shape=(4, B)),
@@ -239,7 +254,7 @@ class Engine:
         B = x0.shape[1]
         if B != self.B:
             self.batch_alloc(B)
-        ar = _Arrays(x0, self.device)
+        ar = _Arrays(x0, self.device, self._host_cache)
         T1 = n_sub_total // ratio + 1
         out, res = self._sim_outputs(ar, B, T1, record)
         R = 0 if noise is None else noise.shape[0]
