@@ -780,8 +780,9 @@ static int pull_totals(mpcb_handle *h) {
 #ifdef TEAM_PROFILE
   fprintf(stderr, "[team profile] Mcycles: iterations %.1f checks %.1f rebuilds %.1f post %.1f setup %.1f | team total %.1f\n",
           t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6, t[8] / 1e6, t[9] / 1e6);
-  if (t[0]) fprintf(stderr, "[team profile] cycles per iteration, one thread: A'v %.0f | bar %.0f | S r %.0f | bar %.0f | A xt %.0f | bar %.0f\n",
-                    (double)t[10] / t[0], (double)t[11] / t[0], (double)t[12] / t[0], (double)t[13] / t[0], (double)t[14] / t[0], (double)t[15] / t[0]);
+  if (t[1]) fprintf(stderr, "[team profile] post step, cycles per control step: select/clip/telemetry %.0f | UKF %.0f | refresh/telemetry %.0f\n",
+                    (double)t[10] / t[1], (double)t[11] / t[1], (double)t[12] / t[1]);
+  if (t[1]) fprintf(stderr, "[team profile] inside UKF: predict %.0f | cholesky %.0f | sigma+hx %.0f\n", (double)t[13] / t[1], (double)t[14] / t[1], (double)t[15] / t[1]);
 #endif
   h->ctr.admm_iterations += (int64_t)t[0];
   h->ctr.operator_rebuilds += (int64_t)t[2];

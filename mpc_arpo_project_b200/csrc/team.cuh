@@ -29,6 +29,10 @@
 // Optional cycle breakdown (compile with -DTEAM_PROFILE): thread 0 of every team accumulates clock64()
 // deltas per phase into tot[4..]: 4 iterations, 5 checks, 6 operator rebuilds, 7 post step, 8 lane setup, 9 total.
 #ifdef TEAM_PROFILE
+#define PS_T0 long long ps_t = clock64();
+#define UK_T0 long long uk_t = clock64();
+#define UK_MARK(k) { const long long uk_n = clock64(); if (lid == 0) atomicAdd(&w.dbg[(k)], (unsigned long long)(uk_n - uk_t)); uk_t = uk_n; }
+#define PS_MARK(k) { const long long ps_n = clock64(); if (lid == 0) atomicAdd(&a.tot[10 + (k)], (unsigned long long)(ps_n - ps_t)); ps_t = ps_n; }
 #ifndef TP_TID
 #define TP_TID 0
 #endif
@@ -41,6 +45,10 @@
 #else
 #define TP_DECL
 #define TP_MARK(slot)
+#define PS_T0
+#define PS_MARK(k)
+#define UK_T0
+#define UK_MARK(k)
 #define TP_PH0
 #define TP_PH(slot)
 #define TP_FLUSH
@@ -108,6 +116,7 @@ struct UkfScratch {
   double Ao[36], Bou[12], Qw[36];      // shared copies: per-thread indexed reads of kernel parameters serialise
   double U[36], sig[78], sf[78], xm[6], Pm[36], zs[26], zp[2], S[4], Pxz[12], K[12];
   int ok;
+  unsigned long long *dbg;             // TEAM_PROFILE builds: cycle counters
 };
 
 __device__ __forceinline__ int ctx_params(const SimConst &c, LaneCtx &L, const double *xe) {
@@ -127,35 +136,81 @@ __device__ __forceinline__ void ukf_sigma_warp(const double *x, const double *U,
   }
 }
 
+// chol_upper6 with the matrix pulled into registers first and every loop unrolled: the shared-memory
+// version serialises ~100 dependent LDS round trips, and sqrt + divisions cost ~5 000 cycles per call.
+__device__ __forceinline__ bool chol_upper6_reg(const double *Psm, double s, double *Usm) {
+  double P[36], U[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    P[i] = Psm[i];
+    U[i] = 0.0;
+  }
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double d = s * P[i * 6 + i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) d -= U[k * 6 + i] * U[k * 6 + i];
+    if (d > 0.0) {
+      const double rinv = rsqrt(d);             // one reciprocal square root instead of a sqrt and 5 divisions:
+      U[i * 6 + i] = d * rinv;                  // differs from sqrt(d), v / sqrt(d) by an ulp
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j) {
+        double v = s * P[i * 6 + j];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= U[k * 6 + i] * U[k * 6 + j];
+        U[i * 6 + j] = v * rinv;
+      }
+    } else {
+      ok = false;                               // row i stays zero (see chol_upper6)
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 36; ++i) Usm[i] = U[i];
+  return ok;
+}
+
 __device__ __noinline__ bool ukf_step_warp(const SimConst &c, double *x, double *P, double u0, double u1, double z0, double z1,
                                            UkfScratch &w, int lid) {
-  if (lid == 0) w.ok = chol_upper6(P, UKF_NPL, w.U) ? 1 : 0;
-  __syncwarp();
-  ukf_sigma_warp(x, w.U, w.sig, lid);
-  __syncwarp();
-  for (int idx = lid; idx < 78; idx += 32) {
-    const int k = idx / 6, i = idx - 6 * k;
+  // predict.  The process model is linear (fx = Ao x + Bou u, trajectorySimulate.py:121-123), so its
+  // unscented transform is evaluated directly: x- = Ao x + Bou u, P- = Ao P Ao' + Q.  This is what
+  // the 13 propagated sigma points sum to (the +/- pairs cancel every cross term; the centre point
+  // contributes Wc0 * eps eps' with eps ~ 1e-12) up to rounding at the 1e-16 level, without the
+  // first Cholesky, the 78 propagations and the two 13-term weighted sums.
+  UK_T0
+  if (lid == 0) w.ok = 1;
+  if (lid < 6) {
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) acc += w.Ao[i * 6 + j] * w.sig[k * 6 + j];
-    w.sf[idx] = acc + w.Bou[i * 2] * u0 + w.Bou[i * 2 + 1] * u1;
+    for (int j = 0; j < 6; ++j) acc += w.Ao[lid * 6 + j] * x[j];
+    w.xm[lid] = acc + w.Bou[lid * 2] * u0 + w.Bou[lid * 2 + 1] * u1;
   }
-  __syncwarp();
-  if (lid < 6) {
-    double acc = UKF_WM0 * w.sf[lid];
-    for (int k = 1; k < 13; ++k) acc += UKF_WI * w.sf[k * 6 + lid];
-    w.xm[lid] = acc;
-  }
-  __syncwarp();
-  for (int idx = lid; idx < 36; idx += 32) {
+  for (int idx = lid; idx < 36; idx += 32) {          // T = Ao P   (kept in w.sig)
     const int i = idx / 6, j = idx - 6 * i;
     double acc = 0.0;
-    for (int k = 0; k < 13; ++k) acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.sf[k * 6 + i] - w.xm[i]) * (w.sf[k * 6 + j] - w.xm[j]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += w.Ao[i * 6 + k] * P[k * 6 + j];
+    w.sig[idx] = acc;
+  }
+  __syncwarp();
+  for (int idx = lid; idx < 36; idx += 32) {          // P- = T Ao' + Q
+    const int i = idx / 6, j = idx - 6 * i;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += w.sig[i * 6 + k] * w.Ao[j * 6 + k];
     w.Pm[idx] = acc + w.Qw[idx];
   }
   __syncwarp();
-  if (lid == 0) w.ok &= chol_upper6(w.Pm, UKF_NPL, w.U) ? 1 : 0;
+  UK_MARK(13)
+  // Two Cholesky factorisations side by side: lane 0 factors 0.05 P- (the sigma points of the update),
+  // lane 1 factors 0.05 P only to learn whether filterpy's predict would have raised on a non-positive
+  // pivot (the lane is reported).  Same instruction stream, different data.
+  if (lid < 2) {
+    const bool ok = chol_upper6_reg(lid == 0 ? w.Pm : P, UKF_NPL, lid == 0 ? w.U : w.sf);
+    if (!ok) w.ok = 0;
+  }
   __syncwarp();
+  UK_MARK(14)
   ukf_sigma_warp(w.xm, w.U, w.sf, lid);          // filterpy 1.4.5 regenerates the points after predict
   __syncwarp();
   if (lid < 13) {
@@ -164,8 +219,10 @@ __device__ __noinline__ bool ukf_step_warp(const SimConst &c, double *x, double 
     w.zs[lid * 2 + 1] = atan2(b, a);
   }
   __syncwarp();
+  UK_MARK(15)
   if (lid < 2) {
     double acc = 0.0;
+#pragma unroll
     for (int k = 0; k < 13; ++k) acc += (k == 0 ? UKF_WM0 : UKF_WI) * w.zs[k * 2 + lid];
     w.zp[lid] = acc;
   }
@@ -174,11 +231,13 @@ __device__ __noinline__ bool ukf_step_warp(const SimConst &c, double *x, double 
     double acc = 0.0;
     if (lid < 4) {
       const int r = lid >> 1, q = lid & 1;
+#pragma unroll
       for (int k = 0; k < 13; ++k)
         acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.zs[k * 2 + r] - w.zp[r]) * (w.zs[k * 2 + q] - w.zp[q]);
       w.S[lid] = acc;
     } else {
       const int e = lid - 4, i = e >> 1, q = e & 1;
+#pragma unroll
       for (int k = 0; k < 13; ++k)
         acc += (k == 0 ? UKF_WC0 : UKF_WI) * (w.sf[k * 6 + i] - w.xm[i]) * (w.zs[k * 2 + q] - w.zp[q]);
       w.Pxz[e] = acc;
@@ -211,6 +270,7 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
   const int ln = L.lane, T1 = a.out.T1, i = L.step;
   const double up0 = L.unext[0], up1 = L.unext[1];               // ctrls[:, i], the command chosen one step ago
   double xn[4];
+  PS_T0
   plant_lin(c, L.xtrue, L.unext, L.noise, xn);                   // every lane of the warp: cheap, avoids a broadcast
   __syncwarp();
   if (lid == 0) {
@@ -257,6 +317,7 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
     for (int k = 0; k < 4; ++k) L.xfin[k] = L.xtrue[k];
   }
   __syncwarp();
+  PS_MARK(0)
   double xe[6];
   if (c.has_noise) {
     const double z0 = sqrt(xn[0] * xn[0] + xn[1] * xn[1]), z1 = atan2(xn[1], xn[0]);
@@ -268,6 +329,7 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
     xe[4] = xe[5] = 0.0;
   }
   __syncwarp();
+  PS_MARK(1)
   if (lid == 0) {
     L.variant = ctx_params(c, L, xe);
     if (c.in_track) {                                            // in-place x/y swap of the stored estimate, simhelpers.py:72
@@ -295,6 +357,7 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
     }
   }
   __syncwarp();
+  PS_MARK(2)
 }
 
 __device__ __noinline__ void lane_init(const TeamArgs &a, LaneCtx &L, int ln) {
@@ -430,6 +493,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   if (tid < NP2 - N) { rbuf[N + tid] = 0.0; xtbuf[N + tid] = 0.0; dk[N + tid] = 0.0; }
   if (tid < 36) { ukf.Ao[tid] = a.sc.Ao[tid]; ukf.Qw[tid] = a.sc.Qw[tid]; }
   if (tid < 12) ukf.Bou[tid] = a.sc.Bou[tid];
+  if (tid == 0) ukf.dbg = a.tot;
   for (int o = tid; o < SS * NCT; o += TEAM) Ssm[o] = 0.0;
   __syncthreads();
 
@@ -620,14 +684,11 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         // ---- check_every ADMM iterations
         const int last_it = a.check_every - 1;
         for (int it = 0; it <= last_it; ++it) {
-          TP_PH0
           if (col_warp) {
             const double s = applyAT(vbuf);
             if (has_col && half == 0) rbuf[col] = sigma * x - qv[col] + s;
           }
-          TP_PH(5)
           __syncthreads();
-          TP_PH(6)
           if (col_warp) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
@@ -659,9 +720,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             if (has_col && half == 0) xtbuf[col] = xt;
             x = alpha * xt + oma * x;
           }
-          TP_PH(7)
           __syncthreads();
-          TP_PH(8)
           if (has_row) {
             const double zt = applyA(xtbuf);
             const double zr = alpha * zt + oma * z;
@@ -672,9 +731,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             vbuf[row] = rv * zn - y;
             if (it == last_it) dybuf[tid] = dy;        // only the block's last delta_y feeds the infeasibility test
           }
-          TP_PH(9)
           __syncthreads();
-          TP_PH(10)
         }
         iter += a.check_every;
         my_iters += (unsigned long long)a.check_every;
