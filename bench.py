@@ -360,6 +360,12 @@ def main():
         _lib.check(lib.mpcb_measure_fp64_peak(local, 1, peak_dmma.ctypes.data_as(_lib.c_double_p)))
         peak = float(max(peak_dfma[0], peak_dmma[0]))
         achieved = fit * admm_iters / (admm_ms * 1e-3) / 1e12 if admm_ms > 0 else None
+        kern = "team_kernel" if admm_launches <= 2 else "admm_block_kernel"
+        traffic = None
+        try:        # DRAM bytes per launch of that kernel from the committed ncu capture (null if never captured)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kern}:{args.workload}")
+        except Exception:
+            pass
         status = res.stats
         line = {
             "metric": METRIC, "value": solves / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -377,8 +383,8 @@ def main():
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "team_kernel (whole closed loop)" if admm_launches <= 2 else "admm_block_kernel",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": kern + (" (whole closed loop, one launch per step)" if kern == "team_kernel" else ""),
                          "algorithmic_flops_per_iteration": fit,
                          "launches": int(admm_launches), "avg_launch_ms": admm_ms / max(1, admm_launches),
                          "share_of_step": admm_ms / step_ms_timed if step_ms_timed else None,
