@@ -92,6 +92,11 @@ typedef struct mpcb_sim_out {
   int16_t *iters;        /* [T1-1][B]  ADMM iterations per solve */
   double *u_raw;         /* [2][T1-1][B] selected control before the norm clip (:314) */
   int32_t *ukf_clamped;  /* [B]  1 if a UKF Cholesky pivot was <= 0 and clamped (the reference raises LinAlgError there) */
+  /* continuous simulator only: telemetry at EVERY substep, the reference's own array shapes
+   * (src/trajectorySimulateC.py:284-292, 414-443); NS = n_sub_total.  Meant for small batches. */
+  double *x_true_sub;    /* [4][NS][B]  xtrueP */
+  double *ctrl_sub;      /* [2][NS][B]  ctrls */
+  uint8_t *ctrlr_sub;    /* [NS][B]     controllerSeq codes 0/1/2 */
 } mpcb_sim_out;
 
 /* Run counters filled by the simulate / qp_solve calls (for bench.py's gpu_launches etc.). */

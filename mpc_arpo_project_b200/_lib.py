@@ -44,6 +44,7 @@ class MpcbSimOut(C.Structure):
         ("x_true", C.c_void_p), ("x_est", C.c_void_p), ("ctrl", C.c_void_p),
         ("ctrlr_seq", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p), ("u_raw", C.c_void_p),
         ("ukf_clamped", C.c_void_p),
+        ("x_true_sub", C.c_void_p), ("ctrl_sub", C.c_void_p), ("ctrlr_sub", C.c_void_p),
     ]
 
 

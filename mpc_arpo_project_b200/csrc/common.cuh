@@ -72,7 +72,8 @@ struct LaneSim {            // SoA [field][B] per-lane simulation state
 struct SimOutDev {
   int32_t *i_term; int32_t *is_success; int32_t *ukf_clamped; double *final_dist;
   double *x_true, *x_est, *ctrl; uint8_t *ctrlr_seq; int8_t *status; int16_t *iters; double *u_raw;
-  int T1;
+  double *x_true_sub, *ctrl_sub; uint8_t *ctrlr_sub;   // continuous simulator, every substep: [.][NS][B]
+  int T1, NS;
 };
 
 enum : int { MODE_QP_ONLY = 0, MODE_DISCRETE = 1, MODE_CONTINUOUS = 2 };

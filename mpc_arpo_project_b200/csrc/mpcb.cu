@@ -997,6 +997,16 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   RC(st.out(o.iters, (T1 - 1) * B, io_on_device, &od.iters));
   RC(st.out(o.u_raw, 2 * (T1 - 1) * B, io_on_device, &od.u_raw));
   RC(st.out(o.ukf_clamped, (size_t)B, io_on_device, &od.ukf_clamped));
+  const size_t NS = (mode == MODE_CONTINUOUS) ? (size_t)n_sub_total : 0;
+  od.NS = (int)NS;
+  if (mode == MODE_CONTINUOUS) {
+    RC(st.out(o.x_true_sub, 4 * NS * B, io_on_device, &od.x_true_sub));
+    RC(st.out(o.ctrl_sub, 2 * NS * B, io_on_device, &od.ctrl_sub));
+    RC(st.out(o.ctrlr_sub, NS * B, io_on_device, &od.ctrlr_sub));
+    if (od.x_true_sub) CK(cudaMemsetAsync(od.x_true_sub, 0xff, 4 * NS * B * 8, h->stream));
+    if (od.ctrl_sub) CK(cudaMemsetAsync(od.ctrl_sub, 0xff, 2 * NS * B * 8, h->stream));
+    if (od.ctrlr_sub) CK(cudaMemsetAsync(od.ctrlr_sub, 0, NS * B, h->stream));
+  }
   // lanes that stop early leave the rest of their telemetry columns undefined in the reference
   // (np.empty, :258-262); here they read NaN / 0
   if (od.x_true) CK(cudaMemsetAsync(od.x_true, 0xff, 4 * T1 * B * 8, h->stream));
@@ -1055,6 +1065,11 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   RC(st.back(o.iters, od.iters, (T1 - 1) * B, io_on_device, h->stream));
   RC(st.back(o.u_raw, od.u_raw, 2 * (T1 - 1) * B, io_on_device, h->stream));
   RC(st.back(o.ukf_clamped, od.ukf_clamped, (size_t)B, io_on_device, h->stream));
+  if (mode == MODE_CONTINUOUS) {
+    RC(st.back(o.x_true_sub, od.x_true_sub, 4 * NS * B, io_on_device, h->stream));
+    RC(st.back(o.ctrl_sub, od.ctrl_sub, 2 * NS * B, io_on_device, h->stream));
+    RC(st.back(o.ctrlr_sub, od.ctrlr_sub, NS * B, io_on_device, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));

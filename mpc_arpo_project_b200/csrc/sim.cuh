@@ -294,6 +294,14 @@ __global__ void init_kernel(const __grid_constant__ PostArgs a, const double *__
     if (a.out.ctrl) for (int i = 0; i < 2; ++i) a.out.ctrl[((size_t)i * T1) * B + ln] = 0.0;
     const int first = (a.mode == MODE_CONTINUOUS) ? a.ratio : 0;
     a.ls.sub[ln] = first;
+    if (a.mode == MODE_CONTINUOUS) {            // xtrueP[:, :ratio+1] = x0, ctrls[:, :ratio+1] = 0, seq[:ratio] = 0 (:289-292, :434)
+      const size_t NS = a.out.NS;
+      const int nfill = min(a.ratio + 1, a.n_sub_total);
+      for (int s = 0; s < nfill; ++s) {
+        if (a.out.x_true_sub) for (int i = 0; i < 4; ++i) a.out.x_true_sub[((size_t)i * NS + s) * B + ln] = x[i];
+        if (a.out.ctrl_sub) for (int i = 0; i < 2; ++i) a.out.ctrl_sub[((size_t)i * NS + s) * B + ln] = 0.0;
+      }
+    }
     const bool nothing = (a.mode == MODE_CONTINUOUS) ? (first >= a.n_sub_total - 1) : (a.nsteps <= 0);
     if (nothing) {
       a.ls.iterm[ln] = (a.mode == MODE_CONTINUOUS) ? a.n_sub_total : a.nsteps;
@@ -418,6 +426,16 @@ __global__ void post_kernel(const __grid_constant__ PostArgs a) {
         variant = estimate_and_refresh(a, ln, xn, uprev, i + 1);
         if (a.out.x_true)
           for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1 + i + 1) * B + ln] = xn[k];
+        const size_t NS = a.out.NS;
+        auto put_sub = [&](int s) {               // substep s done: xtrueP[:, s+1], ctrls[:, s+1], seq[s]
+          if (a.out.x_true_sub) for (int k = 0; k < 4; ++k) a.out.x_true_sub[((size_t)k * NS + s + 1) * B + ln] = xn[k];
+          if (a.out.ctrl_sub) {
+            a.out.ctrl_sub[((size_t)0 * NS + s + 1) * B + ln] = u[0];
+            a.out.ctrl_sub[((size_t)1 * NS + s + 1) * B + ln] = u[1];
+          }
+          if (a.out.ctrlr_sub) a.out.ctrlr_sub[(size_t)s * B + ln] = (uint8_t)code;
+        };
+        put_sub(sub);
         sub += 1;
         const int next_sample = (i + 2) * a.ratio;
         const bool more_samples = (i + 2) < a.nsteps;       // disc_j < nsimD (:335)
@@ -439,6 +457,7 @@ __global__ void post_kernel(const __grid_constant__ PostArgs a) {
           else rk4_substep(xn, 0.0, 0.0, nm, h);
           xn[0] += w0;
           xn[1] += w1;
+          put_sub(sub);
           sub += 1;
         }
         a.ls.sub[ln] = sub;

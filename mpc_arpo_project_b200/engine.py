@@ -206,7 +206,7 @@ class Engine:
         return x
 
     # ------------------------------------------------------------------ closed loops
-    def _sim_outputs(self, ar: _Arrays, B: int, T1: int, record: Sequence[str]):
+    def _sim_outputs(self, ar: _Arrays, B: int, T1: int, record: Sequence[str], NS: int = 0):
         out = _lib.MpcbSimOut()
         res = {}
         spec = {
@@ -215,6 +215,7 @@ class Engine:
             "x_true": ((4, T1, B), np.float64), "x_est": ((6, T1, B), np.float64), "ctrl": ((2, T1, B), np.float64),
             "ctrlr_seq": ((T1 - 1, B), np.uint8), "status": ((T1 - 1, B), np.int8), "iters": ((T1 - 1, B), np.int16),
             "u_raw": ((2, T1 - 1, B), np.float64),
+            "x_true_sub": ((4, NS, B), np.float64), "ctrl_sub": ((2, NS, B), np.float64), "ctrlr_sub": ((NS, B), np.uint8),
         }
         for name in ("i_term", "is_success", "final_dist", "ukf_clamped") + tuple(record):
             shape, dt = spec[name]
@@ -231,7 +232,8 @@ class Engine:
         return BatchSimRun(i_term=res["i_term"], isSuccess=res["is_success"], final_dist=res["final_dist"],
                            x_true=res.get("x_true"), x_est=res.get("x_est"), ctrl_hist=res.get("ctrl"),
                            ctrlr_seq=res.get("ctrlr_seq"), status=res.get("status"), iters=res.get("iters"),
-                           u_raw=res.get("u_raw"), ukf_clamped=res["ukf_clamped"], stats=dict(zip(keys, stats.tolist())),
+                           u_raw=res.get("u_raw"), ukf_clamped=res["ukf_clamped"], x_true_sub=res.get("x_true_sub"),
+                           ctrl_sub=res.get("ctrl_sub"), ctrlr_sub=res.get("ctrlr_sub"), stats=dict(zip(keys, stats.tolist())),
                            stats_vec=stats)
 
     def simulate_discrete(self, x0, noise=None, nsteps: Optional[int] = None, record: Sequence[str] = _RECORD_ALL) -> BatchSimRun:
@@ -256,7 +258,7 @@ class Engine:
             self.batch_alloc(B)
         ar = _Arrays(x0, self.device, self._host_cache)
         T1 = n_sub_total // ratio + 1
-        out, res = self._sim_outputs(ar, B, T1, record)
+        out, res = self._sim_outputs(ar, B, T1, record, int(n_sub_total))
         R = 0 if noise is None else noise.shape[0]
         _lib.check(self.lib.mpcb_simulate_continuous(self._h, B, int(n_sub_total), int(ratio), float(T_cont),
                                                      ar.ptr(x0, shape=(4, B)),

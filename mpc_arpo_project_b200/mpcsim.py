@@ -132,6 +132,9 @@ class BatchSimRun:
     iters: Optional[np.ndarray] = None
     u_raw: Optional[np.ndarray] = None
     ukf_clamped: Optional[np.ndarray] = None     # [B] 1 where the reference's UKF would have raised LinAlgError
+    x_true_sub: Optional[np.ndarray] = None      # continuous simulator, every substep: [4, NS, B] (record 'x_true_sub')
+    ctrl_sub: Optional[np.ndarray] = None        # [2, NS, B]
+    ctrlr_sub: Optional[np.ndarray] = None       # [NS, B]
     stats: dict = field(default_factory=dict)
     stats_vec: Optional[np.ndarray] = None       # the MPCB_NSTATS doubles ranks all-reduce (sum)
 

@@ -85,9 +85,9 @@ def trajectorySimulateC(sim_conditions, mpc_params, fail_params, debris):
     """Reference signature, one trajectory (``src/trajectorySimulateC.py:17-26``).
 
     Like the reference this leaves the global numpy RNG unseeded (``:28`` is commented out) and draws
-    the disturbance sequence from it in ``ct.white_noise``'s order.  ``x_true_pcw``, ``ctrl_hist`` and
-    ``ctrlr_seq`` are returned at the controller's sample instants (every ``int(T/T_cont)``-th substep)
-    rather than at every substep; ``i_term`` is in substeps like the reference's.
+    the disturbance sequence from it in ``ct.white_noise``'s order.  ``x_true_pcw`` (4 x i_term),
+    ``ctrl_hist`` (2 x nsimC) and ``ctrlr_seq`` (i_term) are at every ``T_cont`` substep like the reference's
+    (``:414-443``); entries the reference leaves uninitialised (``np.empty``) are NaN here.
     """
     nsimD, nsimC, ratio = continuous_grid(sim_conditions)
     n_refresh, hold = noise_plan(sim_conditions)
@@ -103,8 +103,11 @@ def trajectorySimulateC(sim_conditions, mpc_params, fail_params, debris):
         for j in range(n_refresh):                                                # :304-307
             sum_vec[:, j * nl:nl * (1 + j)] = ratio * np.concatenate([V[:, j], np.zeros(2)]).reshape(-1, 1)
     x0 = np.asarray(sim_conditions.x0, float).reshape(1, 4)
-    b = trajectorySimulateCBatch(sim_conditions, mpc_params, fail_params, debris, x0, nb)
+    b = trajectorySimulateCBatch(sim_conditions, mpc_params, fail_params, debris, x0, nb,
+                                 record=("x_est", "x_true_sub", "ctrl_sub", "ctrlr_sub"))
     it = int(b.i_term[0])
-    nsamp = min(it // ratio + 1, b.x_true.shape[1])
-    return SimRun(it, bool(b.isSuccess[0]), b.x_true[:, :nsamp, 0].copy(), b.x_est[:, :, 0].copy(),
-                  b.ctrl_hist[:, :nsamp, 0].copy(), b.ctrlr_seq[:max(nsamp - 1, 0), 0].astype(float), sum_vec)
+    seq = b.ctrlr_sub[:it, 0].astype(float)
+    if it >= 2:
+        seq[-1] = seq[-2]                                                         # :443
+    return SimRun(it, bool(b.isSuccess[0]), b.x_true_sub[:, :it, 0].copy(), b.x_est[:, :, 0].copy(),
+                  b.ctrl_sub[:, :, 0].copy(), seq, sum_vec)

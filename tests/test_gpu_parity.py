@@ -282,3 +282,90 @@ def test_full_size_config2_properties():
     # equalities there (u - l < 1e-4 after scaling), which the shared operator does not model; they
     # are counted, not hidden
     assert int(got.stats['flip_lanes']) <= B // 500
+
+
+@pytest.mark.parametrize("name", [k for k, v in GOLDEN_CASES.items() if v[0] == 'C'])
+def test_drop_in_continuous_matches_reference_driver_fixture(name):
+    """trajectorySimulateC(...) -> SimRun (telemetry at every T_cont substep, the reference's array
+    shapes) against the fixture captured from the reference's src/trajectorySimulateC.py (legacy-RNG
+    noise with seed 321; the fixture keeps every 50th substep)."""
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"), allow_pickle=False)
+    sc, mp, fp, debris = make_params(M, GOLDEN_CASES[name][1])
+    np.random.seed(321)
+    r = M.trajectorySimulateC(sc, mp, fp, debris)
+    it = int(g["i_term"])
+    assert r.i_term == it
+    assert bool(r.isSuccess) == bool(g["isSuccess"])
+    nsimC = int(sc.T_final / sc.T_cont)
+    assert r.x_true_pcw.shape == (4, it) and r.ctrl_hist.shape == (2, nsimC) and r.ctrlr_seq.shape == (it,)
+    assert r.x_est.shape == g["x_est"].shape
+    np.testing.assert_allclose(r.x_true_pcw[:, ::50], g["x_true_pcw"], rtol=X_RTOL, atol=X_ATOL)
+    np.testing.assert_allclose(r.ctrl_hist[:, :it:50], g["ctrl_hist"], rtol=0, atol=U_ATOL)
+    np.testing.assert_array_equal(r.ctrlr_seq[::50], g["ctrlr_seq"])
+    nd = int(np.isfinite(g["x_est"][0]).sum())
+    fin = np.isfinite(g["noise_hist"])
+    np.testing.assert_allclose(r.noise_hist[fin], g["noise_hist"][fin], rtol=0, atol=1e-12)
+    # the estimate columns the reference filled (one per executed solve + the initial one)
+    ns = (it - 1) // int(sc.time_stp / sc.T_cont)
+    np.testing.assert_allclose(r.x_est[:, :ns], g["x_est"][:, :ns], rtol=X_RTOL, atol=X_ATOL)
+
+
+def test_continuous_full_rate_telemetry_matches_scalar_oracle():
+    case = dict(Nx=10, sigma=0.0012, noise_length=2, T_cont=0.001, T_final=2, isDeltaV=False)
+    sc, mp, fp, _ = make_params(M, case)
+    rng = np.random.default_rng(21)
+    x0 = np.array([[99.0, 9.0, 0., 0.], [101.5, 11.0, 0., 0.]])
+    B = 2
+    n_refresh = np.arange(0, 2, 0.5 * 2).size
+    V = 0.0012 * rng.standard_normal((B, 2, n_refresh))
+    got = M.trajectorySimulateCBatch(sc, mp, fp, None, x0, np.ascontiguousarray(V.transpose(2, 1, 0)),
+                                     record=("x_true_sub", "ctrl_sub", "ctrlr_sub", "x_est"))
+    for b in range(B):
+        sc.x0 = x0[b].copy()
+        r = trajectory_simulate_c(sc, mp, fp, None, V=V[b], integrator='rk4', chol_fail='clamp')
+        it = r.i_term
+        assert got.i_term[b] == it
+        np.testing.assert_allclose(got.x_true_sub[:, :it, b], r.x_true_pcw, rtol=X_RTOL, atol=X_ATOL)
+        np.testing.assert_allclose(got.ctrl_sub[:, :it, b], r.ctrl_hist[:, :it], rtol=0, atol=U_ATOL)
+        seq = got.ctrlr_sub[:it, b].astype(float)
+        seq[-1] = seq[-2]
+        np.testing.assert_array_equal(seq, r.ctrlr_seq)
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_cases_single_lane_short_runs_and_immediate_termination():
+    case = dict(Nx=10, sigma=0.1, noise_length=5, T_final=5)
+    sc, mp, fp, _ = make_params(M, case)
+    # lane 0 starts inside the platform radius (terminates before its first solve, i_term = 0),
+    # lane 1 starts behind the platform (x < r_p - r_tol), lane 2 is a normal lane
+    x0 = np.array([[1.0, 0.5, 0., 0.], [0.5, 8.0, 0., 0.], [100., 10., 0., 0.]])
+    noise = 0.1 * np.random.default_rng(2).standard_normal((3, 2, 3))
+    got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
+    ref = simulate_discrete_batch(sc, mp, fp, x0, noise, chol_fail='clamp')
+    assert list(got.i_term) == list(ref['i_term']) and got.i_term[0] == 0 and got.i_term[1] == 0
+    assert not got.isSuccess[0] and not got.isSuccess[1]
+    assert np.isnan(got.final_dist[0])                   # x_true_pcw[:, -1] of an empty trajectory
+    T = int(ref['i_term'][2])
+    np.testing.assert_allclose(got.ctrl_hist[:, :T + 1, 2].T, ref['ctrl_hist'][:T + 1, 2], rtol=0, atol=U_ATOL)
+    # a single lane, a single control step
+    one = M.trajectorySimulateBatch(sc, mp, fp, None, x0[2:3], noise[:, :, 2:3], nsteps=1)
+    assert one.batch == 1 and one.i_term[0] == 1 and one.ctrl_hist.shape == (2, 2, 1)
+    np.testing.assert_allclose(one.ctrl_hist[:, 1, 0], ref['ctrl_hist'][1, 2], rtol=0, atol=U_ATOL)
+    # zero steps: nothing is solved, nothing terminates
+    zero = M.trajectorySimulateBatch(sc, mp, fp, None, x0[2:3], noise[:, :, 2:3], nsteps=0)
+    assert zero.i_term[0] == 0 and int(zero.stats['qp_solves']) == 0
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    sc, mp, fp, _ = make_params(M, dict(Nx=10, sigma=0.1))
+    eng = M.Engine(M.build_problem(sc, mp, fp, None))
+    with pytest.raises(M._lib.MpcbError):                  # noisy problem without a noise tensor
+        eng.simulate_discrete(np.zeros((4, 8)), None, 5)
+    with pytest.raises(ValueError):                        # wrong shape
+        eng.simulate_discrete(np.zeros((3, 8)), np.zeros((2, 2, 8)), 5)
+    with pytest.raises(M._lib.MpcbError):
+        eng.batch_alloc(0)
+    eng.close()
+    mp.Nx = 50                                             # a horizon the kernels are not instantiated for
+    with pytest.raises(M._lib.MpcbError):
+        M.Engine(M.build_problem(sc, mp, fp, None))
