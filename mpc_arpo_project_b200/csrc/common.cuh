@@ -104,6 +104,14 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// max over the warp of NON-NEGATIVE doubles with two REDUX instructions: for v >= 0 the IEEE bit pattern orders like
+// the (hi, lo) pair of unsigned words, so reduce hi, then lo among the lanes that hold the winning hi.
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -301,7 +301,7 @@ static void set_warps(mpcb_handle *h, int w) {
 typedef void (*team_fn)(const TeamArgs);
 struct TeamShape { int n, m, wa, wat2, wp, ss; team_fn fn; };
 static const TeamShape kTeamShapes[] = {
-  {81, 136, 8, 6, 4, 4, team_kernel<81, 136, 8, 6, 4, 4>},     // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
+  {81, 136, 8, 6, 4, 8, team_kernel<81, 136, 8, 6, 4, 8>},     // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
 };
 static const TeamShape *team_shape_for(int n, int m) {
   for (const TeamShape &t : kTeamShapes)

@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   auto team_max = [&](auto &vals) {                  // vals: double[CNT], CNT <= 12, stays in registers
     constexpr int CNT = sizeof(vals) / sizeof(double);
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) vals[q] = warp_max(vals[q]);
+    for (int q = 0; q < CNT; ++q) vals[q] = warp_max_nonneg(vals[q]);    // every reduced quantity is an absolute value
     __syncthreads();
     if (lid == 0) {
 #pragma unroll
@@ -729,7 +729,13 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             y += dy;
             z = zn;
             vbuf[row] = rv * zn - y;
-            if (it == last_it) dybuf[tid] = dy;        // only the block's last delta_y feeds the infeasibility test
+            if (it == last_it) {                       // only the block's last delta_y feeds the infeasibility test:
+              double d = dy;                           // store it already projected (is_primal_infeasible, OSQP auxil.c)
+              if ((fl & 3) == 3) d = 0.0;
+              else if (fl & 2) d = fmin(d, 0.0);
+              else if (fl & 1) d = fmax(d, 0.0);
+              dybuf[row] = d;
+            }
           }
           __syncthreads();
         }
@@ -742,18 +748,24 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         if (has_col && half == 0) xtbuf[col] = x;
         if (has_row) vbuf[row] = y;
         __syncthreads();
-        double Ax = 0.0, Px = 0.0, dv = 0.0;
-        double mu[6];
+        // One reduction round serves both the termination test and the primal-infeasibility certificate
+        // (||E dy||, ||D^-1 A'dy||, u'dy+ + l'dy-): the certificate's extra A' product is cheaper than the
+        // two barriers a lazy evaluation costs, and most config-2 solves need it.
+        double Ax = 0.0, Px = 0.0, dv = 0.0, l1 = 0.0;
+        double mu[8];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) mu[q] = 0.0;
+        for (int q = 0; q < 8; ++q) mu[q] = 0.0;
         if (has_row) {
           Ax = applyA(xtbuf);
-          const double ei = Einv[row];
+          const double ei = Einv[row], d = dybuf[row];
           mu[0] = fabs(ei * (Ax - z));
           mu[1] = fabs(ei * z);
           mu[2] = fabs(ei * Ax);
+          mu[6] = fabs(Ev[row] * d);
+          l1 = hibuf[tid] * fmax(d, 0.0) + lobuf[tid] * fmin(d, 0.0);
         }
         const double Aty = col_warp ? applyAT(vbuf) : 0.0;
+        const double Atd = col_warp ? applyAT(dybuf) : 0.0;
         if (has_col) {
           Px = applyP(xtbuf);
           dv = qv[col] + Px + Aty;
@@ -761,45 +773,23 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
           mu[3] = fabs(di * dv);
           mu[4] = fabs(di * Px);
           mu[5] = fabs(di * Aty);
+          mu[7] = fabs(di * Atd);
         }
+        l1 = warp_sum(l1);
+        if (lid == 0) red[warp * 16 + 15] = l1;      // slot 15 is not touched by team_max (<= 12 values); its barriers publish it
         team_max(mu);
         const double pri_u = mu[0], nz_u = mu[1], nax_u = mu[2], dua_u = mu[3] * a.cinv, npx_u = mu[4], naty_u = mu[5];
+        const double ndy = mu[6], natdy = mu[7];
+        double lhs = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) lhs += red[w * 16 + 15];
 
-        // ---- check_termination; the primal-infeasibility certificate is built once if needed (uniform branch)
-        bool cert_ready = false;
-        double ndy = 0, lhs = 0, natdy = 0;
         auto check = [&](double k) -> int {
           const double eps_p = k * a.eps_abs + k * a.eps_rel * fmax(nz_u, nax_u);
           const double eps_d = k * a.eps_abs + k * a.eps_rel * a.cinv * fmax(a.qn_unscaled, fmax(naty_u, npx_u));
           const bool prim_ok = pri_u < eps_p, dual_ok = dua_u < eps_d;
           if (prim_ok && dual_ok) return (k > 1.0) ? 2 : 1;
           if (!prim_ok) {
-            if (!cert_ready) {
-              double n1 = 0, l1 = 0;
-              __syncthreads();
-              if (has_row) {
-                double d = dybuf[tid];
-                if ((fl & 3) == 3) d = 0.0;
-                else if (fl & 2) d = fmin(d, 0.0);
-                else if (fl & 1) d = fmax(d, 0.0);
-                vbuf[row] = d;
-                n1 = fabs(Ev[row] * d);
-                l1 = hibuf[tid] * fmax(d, 0.0) + lobuf[tid] * fmin(d, 0.0);
-              }
-              l1 = warp_sum(l1);
-              __syncthreads();
-              if (lid == 0) red[warp * 16 + 15] = l1;
-              const double atdy = col_warp ? applyAT(vbuf) : 0.0;
-              const double n2 = has_col ? fabs(Dinv[col] * atdy) : 0.0;
-              double two[2] = {n1, n2};
-              team_max(two);
-              ndy = two[0];
-              natdy = two[1];
-              lhs = 0.0;
-#pragma unroll
-              for (int w = 0; w < NW; ++w) lhs += red[w * 16 + 15];
-              cert_ready = true;
-            }
             const double eps_i = k * a.eps_pinf;
             if (ndy > MPCB_DIV_TOL && lhs < -eps_i * ndy && natdy < eps_i * ndy) return (k > 1.0) ? 3 : -3;
           }
