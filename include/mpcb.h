@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 1
+#define MPCB_ABI_VERSION 2
 
 typedef enum mpcb_status {
   MPCB_OK = 0,
@@ -48,6 +48,7 @@ typedef enum mpcb_status {
 /* Controller codes of SimRun.ctrlr_seq (src/trajectorySimulate.py:378-385). */
 #define MPCB_CTRL_MPC 1
 #define MPCB_CTRL_FAILSAFE 2
+#define MPCB_CTRL_DEADBEAT 3
 
 typedef struct mpcb_handle mpcb_handle;
 
@@ -76,6 +77,15 @@ typedef struct mpcb_problem {
   /* spectral KKT operator per sign variant: M(rho)^-1 = V diag(1/(1+rho*lam)) V' */
   const double *V;               /* [4*n*n] */
   const double *lam;             /* [4*n]   */
+  /* Debris-avoidance lanes (src/mpcsim.py:99-123, src/simhelpers.py:48-64,80-134): the half-plane row of every
+   * LOS block changes with the estimate each step, so these problems run on the per-lane path, which re-does
+   * OSQP's scaling and factorisation on the device every control step and needs the UNSCALED data.  With
+   * has_debris != 0 the scaled / spectral tables above may be NULL. */
+  int32_t has_debris, scaling;   /* scaling = OSQP `scaling` setting (Ruiz passes, default 10) */
+  double debris_center[2], debris_side, debris_detect;
+  double debris_verts[8];        /* Debris.constructVertArr() rows, rotated [1,2,3,0] for in-track runs (:52-53) */
+  double K_dead[8], Ki_dead[2];  /* deadbeat avoidance law K_total, K_i (src/trajectorySimulate.py:190-203) */
+  const double *P_u, *q_u, *A_u, *l_u, *u_u;   /* unscaled P [n*n], q [n], A [m*n] (C1 = C2 = +1, slope = 0), l, u [m] (+-inf allowed) */
 } mpcb_problem;
 
 /* Per-trajectory outputs of a simulation; any pointer may be NULL (not recorded).

@@ -34,6 +34,10 @@ class MpcbProblem(C.Structure):
         ("P_s", c_double_p), ("q_s", c_double_p), ("A_s", c_double_p), ("l_s", c_double_p), ("u_s", c_double_p),
         ("D", c_double_p), ("E", c_double_p), ("c", C.c_double),
         ("ctype", c_int32_p), ("V", c_double_p), ("lam", c_double_p),
+        ("has_debris", C.c_int32), ("scaling", C.c_int32),
+        ("debris_center", C.c_double * 2), ("debris_side", C.c_double), ("debris_detect", C.c_double),
+        ("debris_verts", C.c_double * 8), ("K_dead", C.c_double * 8), ("Ki_dead", C.c_double * 2),
+        ("P_u", c_double_p), ("q_u", c_double_p), ("A_u", c_double_p), ("l_u", c_double_p), ("u_u", c_double_p),
     ]
 
 
@@ -81,7 +85,7 @@ SYMBOLS = {
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NSTATS = 10
 _lib = None
 

@@ -1,0 +1,543 @@
+// Generic per-lane path: trajectories whose constraint matrix changes CONTINUOUSLY from step to step,
+// i.e. debris-avoidance lanes (reference src/simhelpers.py:48-64, 80-134: the half-plane row
+// C[4,:] = [-slope, 1, 0, 0] of every LOS block is rebuilt from the estimate each control step).
+//
+// The reference then calls prob.update(Ax=...) (src/trajectorySimulate.py:348), on which OSQP re-runs
+// its Ruiz equilibration from scratch and refactors the KKT matrix, so nothing can be shared across
+// lanes or steps.  One CTA owns one lane and does, per control step, what OSQP does on the host:
+//   geometry -> A values -> scale_data (10 Ruiz passes) -> bounds, constraint types, rho vector ->
+//   M = P + sigma I + A' diag(rho_vec) A  (dense, global scratch) -> S = M^-1 (in-place Gauss-Jordan) ->
+//   ADMM with x~ = S r read from L2, termination / infeasibility / adaptive rho as in team.cuh ->
+//   controller select incl. the deadbeat avoidance law (:299-304), clip, plant, UKF, telemetry.
+// Throughput is not the goal here (the shared-operator kernels cover the debris-free families); parity
+// with the oracle's scalar path is (tests/test_gpu_parity.py::test_debris_*).
+#pragma once
+#include "common.cuh"
+#include "sim.cuh"
+
+#define GEN_THREADS 256
+
+struct GenArgs {
+  int n, m, nX, Nx, Nb, Nc, uoff, B, nnzA, nnzP, scaling;
+  // sparsity pattern of A (CSR + CSC view), values for sign variant (+,+) and slope 1
+  const int *rowptr, *colidx, *colptr, *rowidx, *cscpos;
+  const double *baseA;        // [nnzA]
+  const unsigned char *kindA; // 0 constant, 1 carries sign(vx_hat), 2 sign(vy_hat), 3 carries -slope
+  const int *prow, *pcol;     // P in COO (both triangles)
+  const double *pval, *q_u, *l_u, *u_u;
+  double sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol, rho0;
+  int check_every, adaptive, adapt_interval, max_iter;
+  int mode, nsteps;
+  SimConst sc;
+  // debris geometry (src/mpcsim.py:99-123) and the deadbeat law (:190-203)
+  int has_debris;
+  double dcx, dcy, dside, ddetect, verts[8], Kd[8], Kid[2];
+  SimOutDev out;
+  const double *x0, *noise_in, *xhat;
+  int n_refresh;
+  double *xs, *zs, *ys, *rho, *u0;
+  int *iter, *status;
+  int warm;
+  double *scratch;            // [grid][n*n] dense operator per CTA
+  int *queue;
+  unsigned long long *tot;
+  double *stats;
+};
+
+struct GenLane {
+  double xtrue[4], ux[6], uP[36], xstore[6], unext[2], noise[2], xfin[4], u0[2];
+  double xintf, rho, slope, inter, val, dpin[2], xh[4];
+  int step, iterm, succ, nsolve, ukf_clamp, fin, status, iter, lane, c1, c2, side_pos, bound_on;
+};
+
+// simhelpers.py:66-134 for one estimate `xe` (6, in the caller's storage order); fills the per-step QP data.
+__device__ __forceinline__ void gen_geometry(const GenArgs &a, GenLane &L, const double *xe_in) {
+  const SimConst &c = a.sc;
+  double xe[6];
+  for (int k = 0; k < 6; ++k) xe[k] = xe_in[k];
+  L.c1 = (xe[2] >= 0) ? 1 : -1;
+  L.c2 = (xe[3] >= 0) ? 1 : -1;
+  for (int k = 0; k < 4; ++k) L.xh[k] = xe[k];          // the equality rows use the estimate BEFORE the in-track swap (:340-341)
+  double xc0 = xe[0], xc1 = xe[1];                      // xestCalc
+  double cx = a.dcx, cy = a.dcy;
+  double x0s = xe[0], x1s = xe[1];                      // xest after the in-place swap
+  if (c.in_track) {
+    x0s = xe[1];
+    x1s = xe[0];
+    const double t = cx;
+    cx = cy;
+    cy = t;
+  }
+  const double hs = a.dside / 2;
+  bool inside = false, near_ = false;
+  double slope = 0.0, inter = 0.0;
+  if (a.has_debris) {
+    inside = (x0s - (cx + hs) < 0) && (x0s - (cx - hs) > 0);
+    const int v = (x1s >= 0) ? (inside ? 1 : 0) : (inside ? 2 : 3);
+    slope = (xc1 - a.verts[2 * v + 1]) / (xc0 - a.verts[2 * v]);
+    inter = -slope * xc0 + xc1;
+    near_ = (x0s - (cx + hs) < a.ddetect) && (x0s - (cx + hs) > 0);
+  }
+  L.slope = slope;
+  L.inter = inter;
+  L.val = fabs(xc0 - c.xr[0]) + fabs(xc1 - c.xr[1]);
+  L.side_pos = (x1s >= 0) ? 1 : 0;
+  L.bound_on = (inside || near_) ? 1 : 0;
+  L.dpin[0] = c.is_reject ? xe[4] : 0.0;
+  L.dpin[1] = c.is_reject ? xe[5] : 0.0;
+}
+
+__device__ __forceinline__ double gen_limit(double v) {
+  if (v < 1e-4) return 1.0;
+  return v > 1e4 ? 1e4 : v;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __grid_constant__ GenArgs a) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int tid = threadIdx.x, lid = tid & 31, warp = tid >> 5;
+  const int n = a.n, m = a.m, nnzA = a.nnzA, nnzP = a.nnzP;
+  constexpr int T = GEN_THREADS, NW = GEN_THREADS / 32;
+  // ---- shared memory: vectors of length n / m, scaled values, reductions, lane context
+  double *p = reinterpret_cast<double *>(gsm);
+  auto take = [&](int cnt) { double *r = p; p += (cnt + 1) & ~1; return r; };
+  double *x = take(n), *xt = take(n), *rb = take(n), *qs = take(n), *D = take(n), *Dinv = take(n), *cmax = take(n);
+  double *z = take(m), *y = take(m), *v = take(m), *dyb = take(m), *lo = take(m), *hi = take(m), *rv = take(m), *E = take(m),
+         *Einv = take(m), *rmax = take(m);
+  double *As = take(nnzA), *Ps = take(nnzP), *red = take(16 * NW), *fcol = take(n);
+  int *ctype = reinterpret_cast<int *>(take((m + 1) / 2 + 1));
+  GenLane &L = *reinterpret_cast<GenLane *>(p);
+  __shared__ int s_lane;
+  __shared__ double s_c, s_tmp;
+  double *S = a.scratch + (size_t)blockIdx.x * n * n;
+
+  auto team_max = [&](double val) -> double {
+    val = warp_max_nonneg(val);
+    __syncthreads();
+    if (lid == 0) red[warp] = val;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < NW; ++w) r = fmax(r, red[w]);
+    __syncthreads();
+    return r;
+  };
+  auto team_sum = [&](double val) -> double {
+    val = warp_sum(val);
+    __syncthreads();
+    if (lid == 0) red[warp] = val;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < NW; ++w) r += red[w];
+    __syncthreads();
+    return r;
+  };
+  auto Arow = [&](int i, const double *vec) -> double {        // (A_s vec)[i]
+    double acc = 0.0;
+    for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) acc = fma(As[e], vec[a.colidx[e]], acc);
+    return acc;
+  };
+  auto ATcol = [&](int j, const double *vec) -> double {       // (A_s' vec)[j]
+    double acc = 0.0;
+    for (int e = a.colptr[j]; e < a.colptr[j + 1]; ++e) acc = fma(As[a.cscpos[e]], vec[a.rowidx[e]], acc);
+    return acc;
+  };
+
+  unsigned long long my_iters = 0, my_rebuilds = 0;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_lane = atomicAdd(a.queue, 1);
+    __syncthreads();
+    const int ln = s_lane;
+    if (ln >= a.B) break;
+    const size_t B = a.B;
+    // ---------------- lane initial conditions (trajectorySimulate.py:248-269)
+    if (tid == 0) {
+      L.lane = ln; L.rho = a.rho0; L.xintf = 0.0; L.step = 0; L.succ = 0; L.nsolve = 0; L.ukf_clamp = 0; L.fin = 0;
+      L.status = -10; L.iter = 0; L.u0[0] = L.u0[1] = 0.0;
+      double xe[6];
+      if (a.mode == MODE_QP_ONLY) {
+        for (int k = 0; k < 6; ++k) xe[k] = a.xhat[k * B + ln];
+        if (a.warm) L.rho = a.rho[ln];
+        L.iterm = 0;
+      } else {
+        for (int k = 0; k < 4; ++k) xe[k] = a.x0[k * B + ln];
+        xe[4] = xe[5] = 0.0;
+        for (int k = 0; k < 4; ++k) { L.xtrue[k] = xe[k]; L.xfin[k] = nan(""); }
+        for (int k = 0; k < 6; ++k) { L.ux[k] = xe[k]; L.xstore[k] = xe[k]; }
+        for (int k = 0; k < 36; ++k) L.uP[k] = (k % 7 == 0) ? ((k / 7 < 4) ? 1e-20 : 1.0) : 0.0;
+        L.unext[0] = L.unext[1] = 0.0;
+        L.noise[0] = (a.sc.has_noise && a.noise_in) ? a.noise_in[ln] : 0.0;
+        L.noise[1] = (a.sc.has_noise && a.noise_in) ? a.noise_in[B + ln] : 0.0;
+        const int T1 = a.out.T1;
+        if (a.out.x_true) for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1) * B + ln] = xe[k];
+        if (a.out.x_est) for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1) * B + ln] = xe[k];
+        if (a.out.ctrl) for (int k = 0; k < 2; ++k) a.out.ctrl[((size_t)k * T1) * B + ln] = 0.0;
+        L.iterm = a.nsteps;
+        if (a.nsteps <= 0) L.fin = 1;
+        else if (terminated(a.sc, xe)) { L.iterm = 0; L.fin = 1; }
+      }
+      gen_geometry(a, L, xe);
+    }
+    for (int j = tid; j < n; j += T) x[j] = a.warm ? a.xs[(size_t)ln * n + j] : 0.0;
+    for (int i = tid; i < m; i += T) {
+      z[i] = a.warm ? a.zs[(size_t)ln * m + i] : 0.0;
+      y[i] = a.warm ? a.ys[(size_t)ln * m + i] : 0.0;
+    }
+    __syncthreads();
+
+    while (!L.fin) {
+      // ================= prob.update(l,u); prob.update(Ax,l,u): values, scale_data, bounds, types =================
+      double rho = L.rho;
+      for (int e = tid; e < nnzA; e += T) {
+        const int k = a.kindA[e];
+        As[e] = a.baseA[e] * (k == 1 ? (double)L.c1 : k == 2 ? (double)L.c2 : k == 3 ? L.slope : 1.0);
+      }
+      for (int e = tid; e < nnzP; e += T) Ps[e] = a.pval[e];
+      for (int j = tid; j < n; j += T) { qs[j] = a.q_u[j]; D[j] = 1.0; }
+      for (int i = tid; i < m; i += T) E[i] = 1.0;
+      if (tid == 0) s_c = 1.0;
+      __syncthreads();
+      for (int pass = 0; pass < a.scaling; ++pass) {              // OSQP scale_data (oracle/osqp_ref.py ruiz_scale)
+        for (int j = tid; j < n; j += T) cmax[j] = 0.0;
+        for (int i = tid; i < m; i += T) rmax[i] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < nnzP; e += T)
+          atomicMax(reinterpret_cast<unsigned long long *>(&cmax[a.pcol[e]]), (unsigned long long)__double_as_longlong(fabs(Ps[e])));
+        for (int i = tid; i < m; i += T) {
+          double rm = 0.0;
+          for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) {
+            const double av = fabs(As[e]);
+            rm = fmax(rm, av);
+            atomicMax(reinterpret_cast<unsigned long long *>(&cmax[a.colidx[e]]), (unsigned long long)__double_as_longlong(av));
+          }
+          rmax[i] = rm;
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += T) cmax[j] = 1.0 / sqrt(gen_limit(cmax[j]));
+        for (int i = tid; i < m; i += T) rmax[i] = 1.0 / sqrt(gen_limit(rmax[i]));
+        __syncthreads();
+        for (int e = tid; e < nnzP; e += T) Ps[e] = cmax[a.prow[e]] * Ps[e] * cmax[a.pcol[e]];
+        for (int i = tid; i < m; i += T) {
+          for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) As[e] = rmax[i] * As[e] * cmax[a.colidx[e]];
+          E[i] *= rmax[i];
+        }
+        for (int j = tid; j < n; j += T) { qs[j] *= cmax[j]; D[j] *= cmax[j]; }
+        __syncthreads();
+        // cost normalisation: c_tmp = 1 / limit(max(mean_j ||P_:j||inf, limit(||q||inf)))
+        for (int j = tid; j < n; j += T) cmax[j] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < nnzP; e += T)
+          atomicMax(reinterpret_cast<unsigned long long *>(&cmax[a.pcol[e]]), (unsigned long long)__double_as_longlong(fabs(Ps[e])));
+        __syncthreads();
+        double part = 0.0, qn = 0.0;
+        for (int j = tid; j < n; j += T) { part += cmax[j]; qn = fmax(qn, fabs(qs[j])); }
+        const double csum = team_sum(part);
+        qn = team_max(qn);
+        double ct = fmax(csum / n, gen_limit(qn));
+        ct = 1.0 / gen_limit(ct);
+        for (int e = tid; e < nnzP; e += T) Ps[e] *= ct;
+        for (int j = tid; j < n; j += T) qs[j] *= ct;
+        if (tid == 0) s_c *= ct;
+        __syncthreads();
+      }
+      const double cinv = 1.0 / s_c;
+      double qn_u = 0.0, qn_s = 0.0;
+      for (int j = tid; j < n; j += T) {
+        Dinv[j] = 1.0 / D[j];
+        qn_u = fmax(qn_u, fabs(Dinv[j] * qs[j]));
+        qn_s = fmax(qn_s, fabs(qs[j]));
+      }
+      qn_u = team_max(qn_u);
+      qn_s = team_max(qn_s);
+      for (int i = tid; i < m; i += T) {
+        Einv[i] = 1.0 / E[i];
+        double l_ = a.l_u[i], u_ = a.u_u[i];
+        if (i < 4) l_ = u_ = -L.xh[i];
+        else if (i >= m - 2) l_ = u_ = L.dpin[i - (m - 2)];
+        else if (i >= a.nX && i < a.nX + 5 * (a.Nb + 1)) {
+          const int jj = (i - a.nX) % 5;
+          if (jj == 3) u_ = L.val;
+          else if (jj == 4 && L.bound_on) {
+            if (L.side_pos) l_ = L.inter; else u_ = L.inter;
+          }
+        }
+        l_ = E[i] * fmax(l_, -1e30);
+        u_ = E[i] * fmin(u_, 1e30);
+        lo[i] = l_;
+        hi[i] = u_;
+        const bool fr = (l_ < -1e26) && (u_ > 1e26);
+        ctype[i] = fr ? -1 : ((u_ - l_ < MPCB_RHO_TOL) ? 1 : 0);
+      }
+      __syncthreads();
+      int iter = 0, st = -10;
+      bool need_op = true;                                        // update(Ax) always refactors
+
+      while (st == -10) {
+        if (need_op) {
+          for (int i = tid; i < m; i += T) rv[i] = ctype[i] == -1 ? MPCB_RHO_MIN : (ctype[i] == 1 ? MPCB_RHO_EQ * rho : rho);
+          for (int o = tid; o < n * n; o += T) S[o] = 0.0;
+          __syncthreads();
+          for (int e = tid; e < nnzP; e += T) atomicAdd(&S[(size_t)a.prow[e] * n + a.pcol[e]], Ps[e]);
+          for (int j = tid; j < n; j += T) atomicAdd(&S[(size_t)j * n + j], a.sigma);
+          for (int i = tid; i < m; i += T) {
+            const int e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+            for (int ea = e0; ea < e1; ++ea) {
+              const double w = rv[i] * As[ea];
+              for (int eb = e0; eb < e1; ++eb) atomicAdd(&S[(size_t)a.colidx[ea] * n + a.colidx[eb]], w * As[eb]);
+            }
+          }
+          __threadfence_block();
+          __syncthreads();
+          // in-place Gauss-Jordan inversion (M is symmetric positive definite: no pivoting)
+          for (int k = 0; k < n; ++k) {
+            for (int i = tid; i < n; i += T) fcol[i] = S[(size_t)i * n + k];
+            __syncthreads();
+            const double piv = 1.0 / fcol[k];
+            for (int j = tid; j < n; j += T) S[(size_t)k * n + j] = (j == k) ? piv : S[(size_t)k * n + j] * piv;
+            __syncthreads();
+            for (int o = tid; o < n * n; o += T) {
+              const int i = o / n, j = o - i * n;
+              if (i == k) continue;
+              const double f = fcol[i];
+              S[o] = (j == k) ? -f * piv : fma(-f, S[(size_t)k * n + j], S[o]);
+            }
+            __syncthreads();
+          }
+          need_op = false;
+          ++my_rebuilds;
+        }
+        for (int i = tid; i < m; i += T) v[i] = rv[i] * z[i] - y[i];
+        __syncthreads();
+        for (int it = 0; it < a.check_every; ++it) {
+          for (int j = tid; j < n; j += T) rb[j] = a.sigma * x[j] - qs[j] + ATcol(j, v);
+          __syncthreads();
+          for (int j = tid; j < n; j += T) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc = fma(S[(size_t)k * n + j], rb[k], acc);   // S symmetric: column read is coalesced
+            xt[j] = acc;
+          }
+          __syncthreads();
+          for (int j = tid; j < n; j += T) x[j] = a.alpha * xt[j] + (1.0 - a.alpha) * x[j];
+          for (int i = tid; i < m; i += T) {
+            const double zt = Arow(i, xt);
+            const double zr = a.alpha * zt + (1.0 - a.alpha) * z[i];
+            const double zn = fmin(fmax(zr + (1.0 / rv[i]) * y[i], lo[i]), hi[i]);
+            const double dy = rv[i] * (zr - zn);
+            y[i] += dy;
+            z[i] = zn;
+            v[i] = rv[i] * zn - y[i];
+            dyb[i] = dy;
+          }
+          __syncthreads();
+        }
+        iter += a.check_every;
+        my_iters += (unsigned long long)a.check_every;
+        // ---- update_info / check_termination / adapt_rho (same arithmetic as team.cuh)
+        for (int i = tid; i < m; i += T) v[i] = y[i];
+        __syncthreads();
+        double mu[12];
+        for (int q = 0; q < 12; ++q) mu[q] = 0.0;
+        double l1 = 0.0;
+        for (int i = tid; i < m; i += T) {
+          const double Ax = Arow(i, x), pv = Ax - z[i], ei = Einv[i];
+          mu[0] = fmax(mu[0], fabs(ei * pv)); mu[1] = fmax(mu[1], fabs(ei * z[i])); mu[2] = fmax(mu[2], fabs(ei * Ax));
+          mu[3] = fmax(mu[3], fabs(pv)); mu[4] = fmax(mu[4], fabs(z[i])); mu[5] = fmax(mu[5], fabs(Ax));
+        }
+        for (int j = tid; j < n; j += T) xt[j] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < nnzP; e += T) atomicAdd(&xt[a.prow[e]], Ps[e] * x[a.pcol[e]]);     // xt <- P x
+        __syncthreads();
+        for (int j = tid; j < n; j += T) {
+          const double Px = xt[j], Aty = ATcol(j, v), dv = qs[j] + Px + Aty, di = Dinv[j];
+          mu[6] = fmax(mu[6], fabs(di * dv)); mu[7] = fmax(mu[7], fabs(di * Px)); mu[8] = fmax(mu[8], fabs(di * Aty));
+          mu[9] = fmax(mu[9], fabs(dv)); mu[10] = fmax(mu[10], fabs(Px)); mu[11] = fmax(mu[11], fabs(Aty));
+        }
+        for (int q = 0; q < 12; ++q) mu[q] = team_max(mu[q]);
+        // primal-infeasibility certificate
+        double n1 = 0.0;
+        for (int i = tid; i < m; i += T) {
+          double d = dyb[i];
+          const bool il = lo[i] < -1e26, iu = hi[i] > 1e26;
+          if (il && iu) d = 0.0;
+          else if (iu) d = fmin(d, 0.0);
+          else if (il) d = fmax(d, 0.0);
+          v[i] = d;
+          n1 = fmax(n1, fabs(E[i] * d));
+          l1 += hi[i] * fmax(d, 0.0) + lo[i] * fmin(d, 0.0);
+        }
+        const double ndy = team_max(n1);
+        const double lhs = team_sum(l1);
+        double n2 = 0.0;
+        for (int j = tid; j < n; j += T) n2 = fmax(n2, fabs(Dinv[j] * ATcol(j, v)));
+        const double natdy = team_max(n2);
+        auto check = [&](double k) -> int {
+          const double eps_p = k * a.eps_abs + k * a.eps_rel * fmax(mu[1], mu[2]);
+          const double eps_d = k * a.eps_abs + k * a.eps_rel * cinv * fmax(qn_u, fmax(mu[8], mu[7]));
+          const bool prim_ok = mu[0] < eps_p, dual_ok = mu[6] * cinv < eps_d;
+          if (prim_ok && dual_ok) return (k > 1.0) ? 2 : 1;
+          if (!prim_ok) {
+            const double eps_i = k * a.eps_pinf;
+            if (ndy > MPCB_DIV_TOL && lhs < -eps_i * ndy && natdy < eps_i * ndy) return (k > 1.0) ? 3 : -3;
+          }
+          return -10;
+        };
+        st = check(1.0);
+        if (st == -10) {
+          if (a.adaptive && (iter % a.adapt_interval == 0)) {
+            const double pr = mu[3] / (fmax(mu[4], mu[5]) + 1e-10);
+            const double du = mu[9] / (fmax(qn_s, fmax(mu[11], mu[10])) + 1e-10);
+            double est = rho * sqrt(pr / (du + 1e-10));
+            est = fmin(fmax(est, MPCB_RHO_MIN), MPCB_RHO_MAX);
+            if (est > rho * a.adapt_tol || est < rho / a.adapt_tol) {
+              rho = est;
+              need_op = true;
+            }
+          }
+          if (iter >= a.max_iter) {
+            st = check(10.0);
+            if (st == -10) st = -2;
+          }
+        }
+        __syncthreads();
+      }
+
+      // ================= rest of the control step (thread 0; trajectorySimulate.py:298-356) =================
+      if (tid == 0) {
+        const SimConst &c = a.sc;
+        L.rho = rho; L.status = st; L.iter = iter;
+        L.u0[0] = D[a.uoff] * x[a.uoff];
+        L.u0[1] = D[a.uoff + 1] * x[a.uoff + 1];
+        if (a.mode == MODE_QP_ONLY) {
+          L.fin = 1;
+        } else {
+          const int T1 = a.out.T1, i = L.step;
+          const double *xs4 = L.xstore;                          // xestO[:4, i] (x/y swapped for in-track)
+          double u[2], uraw[2], xn[4];
+          int code;
+          const double hs = a.dside / 2;
+          if (st != 1) {
+            const bool in_box = a.has_debris && (xs4[0] - (a.dcx + hs) < 0) && (xs4[0] - (a.dcx - hs) > 0) &&
+                                (xs4[1] < a.dcy + hs) && (xs4[1] > a.dcy - hs);
+            if (in_box) {                                        // deadbeat collision avoidance (:300-304)
+              L.xintf = L.xintf + xs4[1] - (a.dcy + hs);
+              for (int r = 0; r < 2; ++r) {
+                double acc = 0.0;
+                for (int j = 0; j < 4; ++j) acc += a.Kd[r * 4 + j] * xs4[j];
+                u[r] = -acc - a.Kid[r] * L.xintf;
+              }
+              code = 3;
+            } else {                                             // failsafe (homing) LQR (:305-309)
+              L.xintf = L.xintf + xs4[0] - c.xr[0];
+              for (int r = 0; r < 2; ++r) {
+                double acc = 0.0;
+                for (int j = 0; j < 4; ++j) acc += c.Kpf[r * 4 + j] * xs4[j];
+                u[r] = -acc - c.Kif[r] * L.xintf;
+              }
+              code = 2;
+            }
+          } else {
+            L.xintf = 0.0;
+            u[0] = L.u0[0];
+            u[1] = L.u0[1];
+            code = 1;
+          }
+          uraw[0] = u[0];
+          uraw[1] = u[1];
+          const double nrm = sqrt(u[0] * u[0] + u[1] * u[1]);
+          if (nrm > c.umax0) {
+            u[0] = u[0] * (c.umax0 / nrm);
+            const double nrm2 = sqrt(u[0] * u[0] + u[1] * u[1]);
+            u[1] = u[1] * (c.umax0 / nrm2);
+          }
+          const double uprev[2] = {L.unext[0], L.unext[1]};
+          L.nsolve += 1;
+          if (a.out.status) a.out.status[(size_t)i * B + ln] = (int8_t)st;
+          if (a.out.iters) a.out.iters[(size_t)i * B + ln] = (int16_t)iter;
+          if (a.out.ctrlr_seq) a.out.ctrlr_seq[(size_t)i * B + ln] = (uint8_t)code;
+          if (a.out.u_raw) {
+            a.out.u_raw[((size_t)0 * (T1 - 1) + i) * B + ln] = uraw[0];
+            a.out.u_raw[((size_t)1 * (T1 - 1) + i) * B + ln] = uraw[1];
+          }
+          if (a.out.ctrl) {
+            a.out.ctrl[((size_t)0 * T1 + i + 1) * B + ln] = u[0];
+            a.out.ctrl[((size_t)1 * T1 + i + 1) * B + ln] = u[1];
+          }
+          L.unext[0] = u[0];
+          L.unext[1] = u[1];
+          if (i >= 1 && success_cond(c, L.xtrue)) L.succ = 1;
+          for (int k = 0; k < 4; ++k) L.xfin[k] = L.xtrue[k];
+          plant_lin(c, L.xtrue, uprev, L.noise, xn);
+          double xe[6];
+          if (c.has_noise) {
+            const double zm[2] = {sqrt(xn[0] * xn[0] + xn[1] * xn[1]), atan2(xn[1], xn[0])};
+            if (!ukf_step(c, L.ux, L.uP, uprev, zm)) L.ukf_clamp = 1;
+            for (int k = 0; k < 6; ++k) xe[k] = L.ux[k];
+          } else {
+            for (int k = 0; k < 4; ++k) xe[k] = xn[k];
+            xe[4] = xe[5] = 0.0;
+          }
+          gen_geometry(a, L, xe);
+          if (c.in_track) {
+            const double t = xe[0];
+            xe[0] = xe[1];
+            xe[1] = t;
+          }
+          for (int k = 0; k < 6; ++k) L.xstore[k] = xe[k];
+          if (a.out.x_est) for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1 + i + 1) * B + ln] = xe[k];
+          if (a.out.x_true) for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1 + i + 1) * B + ln] = xn[k];
+          for (int k = 0; k < 4; ++k) L.xtrue[k] = xn[k];
+          if (c.has_noise && ((i + 1) % c.noise_length == 0)) {
+            const int r = min((i + 1) / c.noise_length, a.n_refresh - 1);
+            L.noise[0] = a.noise_in[((size_t)r * 2 + 0) * B + ln];
+            L.noise[1] = a.noise_in[((size_t)r * 2 + 1) * B + ln];
+          }
+          L.step = i + 1;
+          if (i + 1 >= a.nsteps) L.fin = 1;
+          else if (terminated(c, xn)) { L.iterm = i + 1; L.fin = 1; }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---------------- lane done
+    for (int j = tid; j < n; j += T) a.xs[(size_t)ln * n + j] = x[j];
+    for (int i = tid; i < m; i += T) {
+      a.zs[(size_t)ln * m + i] = z[i];
+      a.ys[(size_t)ln * m + i] = y[i];
+    }
+    if (tid == 0) {
+      a.rho[ln] = L.rho;
+      if (a.mode == MODE_QP_ONLY) {
+        a.status[ln] = L.status;
+        a.iter[ln] = L.iter;
+        a.u0[ln] = L.u0[0];
+        a.u0[B + ln] = L.u0[1];
+        atomicAdd(&a.tot[1], 1ull);
+      } else {
+        double d2 = 0.0;
+        for (int k = 0; k < 4; ++k) {
+          const double d = L.xfin[k] - a.sc.xr[k];
+          d2 += d * d;
+        }
+        const double fd = sqrt(d2);
+        if (a.out.i_term) a.out.i_term[ln] = L.iterm;
+        if (a.out.is_success) a.out.is_success[ln] = L.succ;
+        if (a.out.final_dist) a.out.final_dist[ln] = fd;
+        if (a.out.ukf_clamped) a.out.ukf_clamped[ln] = L.ukf_clamp;
+        const double f = (fd == fd) ? fd : 0.0;
+        atomicAdd(&a.stats[0], f);
+        atomicAdd(&a.stats[1], f * f);
+        if (L.succ) atomicAdd(&a.stats[2], 1.0);
+        atomicAdd(&a.stats[3], 1.0);
+        atomicAdd(&a.stats[4], (double)L.iterm);
+        atomicAdd(&a.stats[5], (double)L.nsolve);
+        if (L.ukf_clamp) atomicAdd(&a.stats[8], 1.0);
+        if (L.iterm < a.nsteps) atomicAdd(&a.stats[9], 1.0);
+        atomicAdd(&a.tot[1], (unsigned long long)L.nsolve);
+      }
+    }
+  }
+  if (tid == 0) {
+    if (my_iters) atomicAdd(&a.tot[0], my_iters);
+    if (my_rebuilds) atomicAdd(&a.tot[2], my_rebuilds);
+  }
+}

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "sim.cuh"
 #include "team.cuh"
+#include "generic.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
@@ -30,6 +31,12 @@ static int fail(int code, const std::string &msg) {
       snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
       return fail(e_ == cudaErrorMemoryAllocation ? MPCB_ERR_NOMEM : MPCB_ERR_CUDA, b_);                 \
     }                                                                                                    \
+  } while (0)
+
+#define RC(call)                 \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_ != MPCB_OK) return rc_; \
   } while (0)
 
 typedef void (*admm_fn)(const AdmmArgs);
@@ -61,6 +68,7 @@ struct HostProblem {
   mpcb_problem p;
   std::vector<double> P_s, q_s, A_s, l_s, u_s, D, E, V, lam;
   std::vector<int32_t> ctype;
+  std::vector<double> P_u, q_u, A_u, l_u, u_u;   // unscaled data (per-lane path)
 };
 
 struct StageBuf {
@@ -94,6 +102,13 @@ struct mpcb_handle {
   size_t team_smem = 0;
   const void *team_fn_ptr = nullptr;
   int team_ctas = 0;
+  // per-lane path (debris lanes)
+  bool generic_ok = false;
+  GenArgs gproto;
+  std::vector<void *> gen_bufs;
+  double *gen_scratch = nullptr;
+  int gen_grid = 0;
+  size_t gen_smem = 0;
   // batch state
   int64_t B = 0;
   double *xs = nullptr, *zs = nullptr, *ys = nullptr, *rho = nullptr, *par = nullptr, *u0 = nullptr;
@@ -501,6 +516,113 @@ static int launch_team(mpcb_handle *h, const TeamArgs &ta) {
   return MPCB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Per-lane path tables: sparsity pattern of A (CSR + CSC view) with entry kinds, P in COO, unscaled vectors.
+template <typename Tv>
+static int gen_upload(mpcb_handle *h, const std::vector<Tv> &v, const Tv **out) {
+  void *d = nullptr;
+  CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(Tv)));
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+  h->gen_bufs.push_back(d);
+  *out = (const Tv *)d;
+  return MPCB_OK;
+}
+
+static int build_generic_tables(mpcb_handle *h) {
+  const HostProblem &hp = h->hp;
+  const mpcb_problem &p = hp.p;
+  const int n = p.n, m = p.m, nX = 4 * (p.Nx + 1);
+  std::vector<int> rowptr(m + 1, 0), colidx, colptr(n + 1, 0), rowidx, cscpos, prow, pcol;
+  std::vector<double> base, pval;
+  std::vector<unsigned char> kind;
+  for (int r = 0; r < m; ++r) {
+    for (int c = 0; c < n; ++c) {
+      double v = hp.A_u[(size_t)r * n + c];
+      unsigned char k = 0;
+      if (r >= nX && r < nX + 5 * (p.Nx + 1)) {
+        const int blk = (r - nX) / 5, jj = (r - nX) % 5;
+        if (jj == 3 && c == 4 * blk + 2) { k = 1; v = fabs(v); }
+        else if (jj == 3 && c == 4 * blk + 3) { k = 2; v = fabs(v); }
+        else if (jj == 4 && c == 4 * blk) { k = 3; v = -1.0; }              // C[4,0] = -slope (simhelpers.py:108)
+      }
+      if (v != 0.0) {
+        colidx.push_back(c);
+        base.push_back(v);
+        kind.push_back(k);
+      }
+    }
+    rowptr[r + 1] = (int)colidx.size();
+  }
+  const int nnz = (int)colidx.size();
+  for (int e = 0; e < nnz; ++e) colptr[colidx[e] + 1]++;
+  for (int c = 0; c < n; ++c) colptr[c + 1] += colptr[c];
+  rowidx.resize(nnz);
+  cscpos.resize(nnz);
+  {
+    std::vector<int> fill(colptr.begin(), colptr.end() - 1);
+    for (int r = 0; r < m; ++r)
+      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+        const int q = fill[colidx[e]]++;
+        rowidx[q] = r;
+        cscpos[q] = e;
+      }
+  }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c)
+      if (hp.P_u[(size_t)r * n + c] != 0.0) {
+        prow.push_back(r);
+        pcol.push_back(c);
+        pval.push_back(hp.P_u[(size_t)r * n + c]);
+      }
+  GenArgs &g = h->gproto;
+  memset(&g, 0, sizeof g);
+  g.n = n; g.m = m; g.nX = nX; g.Nx = p.Nx; g.Nb = p.Nb; g.Nc = p.Nc; g.uoff = nX;
+  g.nnzA = nnz; g.nnzP = (int)pval.size(); g.scaling = p.scaling;
+  RC(gen_upload(h, rowptr, &g.rowptr)); RC(gen_upload(h, colidx, &g.colidx)); RC(gen_upload(h, colptr, &g.colptr));
+  RC(gen_upload(h, rowidx, &g.rowidx)); RC(gen_upload(h, cscpos, &g.cscpos)); RC(gen_upload(h, base, &g.baseA));
+  RC(gen_upload(h, kind, &g.kindA)); RC(gen_upload(h, prow, &g.prow)); RC(gen_upload(h, pcol, &g.pcol));
+  RC(gen_upload(h, pval, &g.pval)); RC(gen_upload(h, hp.q_u, &g.q_u)); RC(gen_upload(h, hp.l_u, &g.l_u));
+  RC(gen_upload(h, hp.u_u, &g.u_u));
+  g.sigma = p.sigma; g.alpha = p.alpha; g.eps_abs = p.eps_abs; g.eps_rel = p.eps_rel; g.eps_pinf = p.eps_prim_inf;
+  g.adapt_tol = p.adaptive_rho_tolerance;
+  g.rho0 = std::min(std::max(p.rho0, MPCB_RHO_MIN), MPCB_RHO_MAX);
+  g.check_every = p.check_termination; g.adaptive = p.adaptive_rho; g.adapt_interval = std::max(1, p.adaptive_rho_interval);
+  g.max_iter = p.max_iter;
+  g.sc = h->sc;
+  g.has_debris = p.has_debris;
+  g.dcx = p.debris_center[0]; g.dcy = p.debris_center[1]; g.dside = p.debris_side; g.ddetect = p.debris_detect;
+  memcpy(g.verts, p.debris_verts, sizeof g.verts);
+  memcpy(g.Kd, p.K_dead, sizeof g.Kd);
+  memcpy(g.Kid, p.Ki_dead, sizeof g.Kid);
+  auto ev = [](int c) { return (size_t)((c + 1) & ~1); };
+  h->gen_smem = 8 * (7 * ev(n) + 10 * ev(m) + ev(nnz) + ev(g.nnzP) + ev(16 * (GEN_THREADS / 32)) + ev(n) + ev((m + 1) / 2 + 1)) +
+                sizeof(GenLane) + 64;
+  if (h->gen_smem > 220 * 1024) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path");
+  CK(cudaFuncSetAttribute((const void *)generic_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gen_smem));
+  h->gen_grid = h->num_sms;
+  CK(cudaMalloc(&h->gen_scratch, (size_t)h->gen_grid * n * n * 8));
+  h->generic_ok = true;
+  return MPCB_OK;
+}
+
+static int launch_generic(mpcb_handle *h, GenArgs &g) {
+  g.B = (int)h->B;
+  g.xs = h->xs; g.zs = h->zs; g.ys = h->ys; g.rho = h->rho; g.u0 = h->u0; g.iter = h->iter; g.status = h->status;
+  g.scratch = h->gen_scratch;
+  g.queue = h->d_queue;
+  g.tot = h->d_tot;
+  g.stats = h->d_stats;
+  const int grid = (int)std::min<int64_t>(h->B, h->gen_grid);
+  CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+  generic_lane_kernel<<<grid, GEN_THREADS, h->gen_smem, h->stream>>>(g);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  h->ctr.admm_launches += 1;
+  h->ctr.rounds += 1;
+  return MPCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" int mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
 extern "C" const char *mpcb_last_error(void) { return g_err.c_str(); }
@@ -513,8 +635,13 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
     return fail(MPCB_ERR_INVALID, "bad horizons");
   if (n != 4 * (pr->Nx + 1) + 7 * pr->Nc + 2 || m != 9 * (pr->Nx + 1) + 7 * pr->Nc + 2)
     return fail(MPCB_ERR_INVALID, "n/m do not match the horizons");
-  if (!pr->P_s || !pr->q_s || !pr->A_s || !pr->l_s || !pr->u_s || !pr->D || !pr->E || !pr->ctype || !pr->V || !pr->lam)
+  const bool debris = pr->has_debris != 0;
+  if (debris) {
+    if (!pr->P_u || !pr->q_u || !pr->A_u || !pr->l_u || !pr->u_u)
+      return fail(MPCB_ERR_INVALID, "debris problems need the unscaled P_u, q_u, A_u, l_u, u_u");
+  } else if (!pr->P_s || !pr->q_s || !pr->A_s || !pr->l_s || !pr->u_s || !pr->D || !pr->E || !pr->ctype || !pr->V || !pr->lam) {
     return fail(MPCB_ERR_INVALID, "null table pointer");
+  }
   if (pr->check_termination < 1 || pr->max_iter % pr->check_termination != 0 ||
       (pr->adaptive_rho && (pr->adaptive_rho_interval < 1 || pr->adaptive_rho_interval % pr->check_termination != 0)))
     return fail(MPCB_ERR_INVALID, "max_iter and adaptive_rho_interval must be multiples of check_termination");
@@ -528,18 +655,27 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
   memset(&h->ls, 0, sizeof h->ls);
   HostProblem &hp = h->hp;
   hp.p = *pr;
-  hp.P_s.assign(pr->P_s, pr->P_s + (size_t)n * n);
-  hp.q_s.assign(pr->q_s, pr->q_s + n);
-  hp.A_s.assign(pr->A_s, pr->A_s + (size_t)m * n);
-  hp.l_s.assign(pr->l_s, pr->l_s + m);
-  hp.u_s.assign(pr->u_s, pr->u_s + m);
-  hp.D.assign(pr->D, pr->D + n);
-  hp.E.assign(pr->E, pr->E + m);
-  hp.V.assign(pr->V, pr->V + (size_t)4 * n * n);
-  hp.lam.assign(pr->lam, pr->lam + (size_t)4 * n);
-  hp.ctype.assign(pr->ctype, pr->ctype + m);
+  if (debris) {
+    hp.P_u.assign(pr->P_u, pr->P_u + (size_t)n * n);
+    hp.q_u.assign(pr->q_u, pr->q_u + n);
+    hp.A_u.assign(pr->A_u, pr->A_u + (size_t)m * n);
+    hp.l_u.assign(pr->l_u, pr->l_u + m);
+    hp.u_u.assign(pr->u_u, pr->u_u + m);
+  } else {
+    hp.P_s.assign(pr->P_s, pr->P_s + (size_t)n * n);
+    hp.q_s.assign(pr->q_s, pr->q_s + n);
+    hp.A_s.assign(pr->A_s, pr->A_s + (size_t)m * n);
+    hp.l_s.assign(pr->l_s, pr->l_s + m);
+    hp.u_s.assign(pr->u_s, pr->u_s + m);
+    hp.D.assign(pr->D, pr->D + n);
+    hp.E.assign(pr->E, pr->E + m);
+    hp.V.assign(pr->V, pr->V + (size_t)4 * n * n);
+    hp.lam.assign(pr->lam, pr->lam + (size_t)4 * n);
+    hp.ctype.assign(pr->ctype, pr->ctype + m);
+  }
   hp.p.P_s = hp.p.q_s = hp.p.A_s = hp.p.l_s = hp.p.u_s = hp.p.D = hp.p.E = hp.p.V = hp.p.lam = nullptr;
   hp.p.ctype = nullptr;
+  hp.p.P_u = hp.p.q_u = hp.p.A_u = hp.p.l_u = hp.p.u_u = nullptr;
   SimConst &sc = h->sc;
   memcpy(sc.Ad, pr->Ad, sizeof sc.Ad);
   memcpy(sc.Bd, pr->Bd, sizeof sc.Bd);
@@ -556,18 +692,21 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
-  int rc = build_tables(h);
+  int rc = MPCB_OK;
+  if (debris) {
+    rc = build_generic_tables(h);
+  } else {
+    rc = build_tables(h);
+    if (rc == MPCB_OK) {
+      set_warps(h, h->warps);
+      rc = build_team_tables(h);
+    }
+  }
   if (rc != MPCB_OK) {
     mpcb_destroy(h);
     return rc;
   }
-  set_warps(h, h->warps);
-  rc = build_team_tables(h);
-  if (rc != MPCB_OK) {
-    mpcb_destroy(h);
-    return rc;
-  }
-  CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  if (!debris) CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&h->d_tot, 16 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_tot, 0, 16 * sizeof(unsigned long long)));
@@ -600,6 +739,8 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
     cudaFree(h->d_V[v]);
   }
   cudaFree(h->d_tot);
+  cudaFree(h->gen_scratch);
+  for (void *q : h->gen_bufs) cudaFree(q);
   for (StageBuf &b : h->stage_pool) cudaFree(b.ptr);
   cudaFree(h->d_tblob);
   cudaFree(h->d_lam);
@@ -837,11 +978,6 @@ struct Stage {
     return MPCB_OK;
   }
 };
-#define RC(call)                 \
-  do {                           \
-    int rc_ = (call);            \
-    if (rc_ != MPCB_OK) return rc_; \
-  } while (0)
 
 __global__ void gather_qp_out_kernel(int B, const int *__restrict__ status, const int *__restrict__ iter,
                                      int32_t *__restrict__ st_out, int32_t *__restrict__ it_out) {
@@ -869,7 +1005,13 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
   fill_args(h, aa, pa, MODE_QP_ONLY);
   CK(cudaEventRecord(h->ev_t0, h->stream));
   const int pgrid = (int)((B + 127) / 128);
-  if (h->team_ok) {
+  if (h->generic_ok) {
+    GenArgs g = h->gproto;
+    g.mode = MODE_QP_ONLY;
+    g.xhat = d_xhat;
+    g.warm = 1;
+    RC(launch_generic(h, g));
+  } else if (h->team_ok) {
     TeamArgs ta;
     fill_team_args(h, ta, MODE_QP_ONLY);
     ta.xhat = d_xhat;
@@ -1030,7 +1172,18 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   pa.n_refresh = n_refresh;
   CK(cudaEventRecord(h->ev_t0, h->stream));
   CK(cudaMemsetAsync(h->d_stats, 0, MPCB_NSTATS * sizeof(double), h->stream));
-  if (h->team_ok && mode == MODE_DISCRETE) {
+  if (h->generic_ok) {
+    if (mode != MODE_DISCRETE) return fail(MPCB_ERR_INVALID, "debris lanes are supported by the discrete simulator only");
+    GenArgs g = h->gproto;
+    g.mode = MODE_DISCRETE;
+    g.nsteps = nsteps;
+    g.out = od;
+    g.x0 = d_x0;
+    g.noise_in = d_noise;
+    g.n_refresh = n_refresh;
+    g.warm = 0;
+    RC(launch_generic(h, g));
+  } else if (h->team_ok && mode == MODE_DISCRETE) {
     TeamArgs ta;
     fill_team_args(h, ta, MODE_DISCRETE);
     ta.nsteps = nsteps;

@@ -118,8 +118,17 @@ class Engine:
             ptr_t = _lib.c_double_p if dtype == np.float64 else _lib.c_int32_p
             setattr(cp, name, a.ctypes.data_as(ptr_t))
 
-        table("P_s", p.P_s); table("q_s", p.q_s); table("A_s", p.A_s); table("l_s", p.l_s); table("u_s", p.u_s)
-        table("D", p.D); table("E", p.E); table("ctype", p.ctype, np.int32); table("V", p.V); table("lam", p.lam)
+        cp.has_debris, cp.scaling = int(p.has_debris), int(st.scaling)
+        if p.has_debris:
+            table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
+            cp.debris_center[:] = np.asarray(p.debris_center, float).tolist()
+            cp.debris_side, cp.debris_detect = float(p.debris_side), float(p.debris_detect)
+            cp.debris_verts[:] = np.asarray(p.debris_verts, float).reshape(-1).tolist()
+        else:
+            table("P_s", p.P_s); table("q_s", p.q_s); table("A_s", p.A_s); table("l_s", p.l_s); table("u_s", p.u_s)
+            table("D", p.D); table("E", p.E); table("ctype", p.ctype, np.int32); table("V", p.V); table("lam", p.lam)
+        cp.K_dead[:] = np.asarray(p.K_dead, float).reshape(-1).tolist()
+        cp.Ki_dead[:] = np.asarray(p.Ki_dead, float).reshape(-1).tolist()
         cp.c = p.c
         _lib.check(self.lib.mpcb_create(C.byref(cp), self.device, C.byref(self._h)))
 

@@ -78,6 +78,17 @@ def _lqr_gain(A, B, Q, R):
     return np.linalg.solve(R + B.T @ X @ B, B.T @ X @ A), X
 
 
+def _ackermann(A, B, poles):
+    """Single-input pole placement by Ackermann's formula (``ct.acker`` in the reference,
+    ``src/trajectorySimulate.py:198``): K = e_n' ctrb(A,B)^-1 p(A)."""
+    n = A.shape[0]
+    B = np.asarray(B, float).reshape(n, 1)
+    ctrb = np.hstack([np.linalg.matrix_power(A, i) @ B for i in range(n)])
+    coef = np.real(np.poly(poles))                   # p(s) = s^n + c1 s^(n-1) + ... + cn
+    pA = sum(coef[i] * np.linalg.matrix_power(A, n - i) for i in range(n + 1))
+    return np.linalg.solve(ctrb, pA)[-1:, :]
+
+
 def _limit(v):
     v = np.where(v < MIN_SCALING, 1.0, v)
     return np.minimum(v, MAX_SCALING)
@@ -102,6 +113,15 @@ def ruiz_equilibrate(P, q, A, passes: int):
         inv = 1.0 / ct
         P, q, c = P * inv, q * inv, c * inv
     return P, q, A, D, E, c
+
+
+def _ukf_process_noise(scale, sc):
+    """UKF process noise (ref :272-275 / C-variant :310-313)."""
+    sig = np.array(sc.noise.noise_std, float) if sc.noise is not None else np.zeros(2)
+    Qw = np.zeros((6, 6))
+    Qw[:4, :4] = 0.001 * np.eye(4)
+    Qw[4, 4], Qw[5, 5] = (scale * sig[0]) ** 2, (scale * sig[1]) ** 2
+    return Qw
 
 
 @dataclass
@@ -157,6 +177,14 @@ class Problem:
     lam: np.ndarray              # [4, n]
     settings: SolverSettings = field(default_factory=SolverSettings)
     u_off: int = 0               # offset of u_0 in the decision vector
+    # debris-avoidance lanes (src/mpcsim.py:99-123): per-lane path, no shared tables
+    has_debris: bool = False
+    debris_center: np.ndarray = field(default_factory=lambda: np.zeros(2))
+    debris_side: float = 0.0
+    debris_detect: float = 0.0
+    debris_verts: np.ndarray = field(default_factory=lambda: np.zeros((4, 2)))
+    K_dead: np.ndarray = field(default_factory=lambda: np.zeros((2, 4)))     # K_total (:199-201)
+    Ki_dead: np.ndarray = field(default_factory=lambda: np.zeros(2))         # K_i (:202)
 
     def A_variant(self, v: int, scaled: bool = True):
         A = (self.A_s if scaled else self.A).copy()
@@ -172,8 +200,6 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
     """Build the constant tables.  ``ukf_interval_scale``: the reference's continuous
     simulator scales the disturbance process noise by ``T*int(T/T_cont)``
     (``trajectorySimulateC.py:310``) instead of ``T`` (``trajectorySimulate.py:272``)."""
-    if debris is not None:
-        raise NotImplementedError("debris-avoidance lanes are not built yet (SURVEY.md section 8(f)-1); pass debris=None")
     st = settings or SolverSettings()
     sc, mp, fp = sim_conditions, mpc_params, fail_params
     Nx, Nc, Nb = int(mp.Nx), int(mp.Nc), int(mp.Nb)
@@ -266,6 +292,34 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
     A[m - 2, n - 2] = A[m - 1, n - 1] = 1.0
     l[m - 2:] = u[m - 2:] = 0.0
 
+    # deadbeat avoidance law on the (y, ydot, int y) subsystem, all poles at 0 (ref :190-203)
+    Ap_ = Ad[[1, 3], :][:, [1, 3]]
+    Bp_ = Bd[[1, 3], 1].reshape(2, 1)
+    Aaug_d = np.block([[Ap_, np.zeros((2, 1))], [np.array([[1.0, 0.0]]), np.eye(1)]])
+    Baug_d = np.vstack([Bp_, np.zeros((1, 1))])
+    Kp_ = _ackermann(Aaug_d, Baug_d, np.zeros(3))
+    K_dead = np.zeros((2, 4))
+    K_dead[1, 1], K_dead[1, 3] = Kp_[0, 0], Kp_[0, 1]
+    Ki_dead = np.array([0.0, Kp_[0, 2]])
+    if debris is not None:
+        # The half-plane row C[4,:] = [-slope, 1, 0, 0] is rebuilt from the estimate every step and OSQP then
+        # re-scales and refactors (ref :345-348): no table can be shared, the device does the whole setup per lane.
+        verts = np.asarray(debris.constructVertArr(), float)
+        if sc.inTrack:
+            verts = verts[[1, 2, 3, 0]]                    # simhelpers.py:52-53
+        return Problem(Nx=Nx, Nc=Nc, Nb=Nb, n=n, m=m, in_track=bool(sc.inTrack), delta_v=bool(sc.isDeltaV),
+                       is_reject=bool(sc.isReject), has_noise=sc.noise is not None, T=T, mean_mtn=nmm,
+                       r_p=float(sc.r_p), r_tol=float(sc.r_tol), xr=xr, umax0=float(mp.u_lim[0]),
+                       suc_dist=float(sc.suc_cond[0]), suc_ang=float(sc.suc_cond[1]),
+                       sig=np.array(sc.noise.noise_std, float) if sc.noise is not None else np.zeros(2),
+                       noise_length=int(sc.noise.noise_length) if sc.noise is not None else 1,
+                       Ad=Ad, Bd=Bd, Ao=Ao, Bou=Bou, Qw=_ukf_process_noise(T if ukf_interval_scale is None else ukf_interval_scale, sc),
+                       Kpf=Kf[:, :4], Kif=Kf[:, 4:5], C=C, P=P, q=q, A=A, l=l, u=u,
+                       D=np.ones(n), E=np.ones(m), c=1.0, P_s=None, q_s=None, A_s=None, l_s=None, u_s=None, ctype=None,
+                       sgn_rows=np.array(sgn_rows), sgn_c1_col=np.array(c1c), sgn_c2_col=np.array(c2c), row3=np.array(row3),
+                       V=None, lam=None, settings=st, u_off=nX, has_debris=True,
+                       debris_center=np.asarray(debris.center, float), debris_side=float(debris.side_length),
+                       debris_detect=float(debris.detect_distance), debris_verts=verts, K_dead=K_dead, Ki_dead=Ki_dead)
     P_s, q_s, A_s, D, E, c = ruiz_equilibrate(P, q, A, st.scaling) if st.scaling else (P, q, A, np.ones(n), np.ones(m), 1.0)
     l_s = E * np.maximum(l, -OSQP_INFTY)
     u_s = E * np.minimum(u, OSQP_INFTY)
@@ -282,13 +336,9 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
                    Ad=Ad, Bd=Bd, Ao=Ao, Bou=Bou, Qw=np.zeros((6, 6)), Kpf=Kf[:, :4], Kif=Kf[:, 4:5], C=C,
                    P=P, q=q, A=A, l=l, u=u, D=D, E=E, c=c, P_s=P_s, q_s=q_s, A_s=A_s, l_s=l_s, u_s=u_s, ctype=ctype,
                    sgn_rows=np.array(sgn_rows), sgn_c1_col=np.array(c1c), sgn_c2_col=np.array(c2c),
-                   row3=np.array(row3), V=np.zeros((4, n, n)), lam=np.zeros((4, n)), settings=st, u_off=nX)
-    # UKF process noise (ref :272-275 / C-variant :310-313)
-    scale = T if ukf_interval_scale is None else ukf_interval_scale
-    Qw = np.zeros((6, 6))
-    Qw[:4, :4] = 0.001 * np.eye(4)
-    Qw[4, 4], Qw[5, 5] = (scale * prob.sig[0]) ** 2, (scale * prob.sig[1]) ** 2
-    prob.Qw = Qw
+                   row3=np.array(row3), V=np.zeros((4, n, n)), lam=np.zeros((4, n)), settings=st, u_off=nX,
+                   K_dead=K_dead, Ki_dead=Ki_dead)
+    prob.Qw = _ukf_process_noise(T if ukf_interval_scale is None else ukf_interval_scale, sc)
 
     # ---- spectral operator per sign variant
     w = np.where(ctype == 1, RHO_EQ_FACTOR, 1.0)

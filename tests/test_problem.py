@@ -49,7 +49,17 @@ def test_spectral_operator_is_the_kkt_inverse(rho):
         np.testing.assert_allclose(Minv @ Mk, np.eye(p.n), rtol=0, atol=2e-9)
 
 
-def test_debris_is_rejected_until_built():
-    sc, mp, fp, debris = make_params(M, dict(Nx=10, sigma=0.1, debris=((40., 0.), 5., 20)))
-    with pytest.raises(NotImplementedError):
-        M.build_problem(sc, mp, fp, debris)
+def test_debris_problem_carries_unscaled_data_and_deadbeat_gains():
+    """Debris problems run on the per-lane path: no shared scaling / spectral tables, unscaled QP with the
+    slope entries left at zero (the device fills them per lane and step), deadbeat gains as in the oracle."""
+    case = dict(Nx=40, sigma=0.75, debris=((40., 0.), 5., 20))
+    sc, mp, fp, debris = make_params(M, case)
+    p = M.build_problem(sc, mp, fp, debris)
+    s = build_setup(sc, mp, fp, debris)
+    assert p.has_debris and p.A_s is None and p.V is None
+    np.testing.assert_allclose(p.K_dead, s.K_total, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(p.Ki_dead, s.K_i.ravel(), rtol=1e-12, atol=1e-14)
+    diff = np.argwhere(np.abs(s.A - p.A) > 1e-12)
+    nX = 4 * (p.Nx + 1)
+    assert len(diff) == p.Nx + 1 and all(r == nX + 5 * k + 4 and c == 4 * k for k, (r, c) in enumerate(diff))
+    np.testing.assert_allclose(p.debris_verts, debris.constructVertArr())
