@@ -1,0 +1,95 @@
+"""Monte-Carlo studies of the reference as single batched calls.
+
+* :func:`final_distance_ratio_sweep` is ``test/disturbRejComp.py:74-100``: for every noise hold length, the
+  mean final distance to the target with disturbance rejection divided by the mean without it.
+* :func:`success_rate` is ``test/saved_runs/success_rates_test.py:64-75``.
+
+The reference re-seeds the global RNG with 123 inside every ``trajectorySimulate`` call
+(``src/trajectorySimulate.py:28``), so its "100 Monte-Carlo runs" per setting are 100 copies of one
+realisation and its rejection / no-rejection runs share that realisation.  Here every lane gets its own
+draw (``numpy.random.default_rng(seed)``), and the rejection / no-rejection batches share the draws lane by
+lane, which keeps the pairing and makes the average a real one.  Under ``torch.distributed`` every rank
+simulates its own ``mc_num`` lanes and the statistics are all-reduced (sum), the path's only collective.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine
+from .mpcsim import Noise
+from .problem import build_problem
+from .trajectorySimulate import n_control_steps, noise_refreshes
+
+
+def _allreduce_sum(vec: np.ndarray, device: int) -> np.ndarray:
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return vec
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return vec
+    dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def _rank() -> int:
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except Exception:
+        return 0
+
+
+def _run(sc, mp, fp, debris, x0, noise, device):
+    eng = Engine(build_problem(sc, mp, fp, debris), device)
+    try:
+        return eng.simulate_discrete(x0, noise, n_control_steps(sc), record=())
+    finally:
+        eng.close()
+
+
+def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, noise_std: Sequence[float],
+                               noise_lengths: Sequence[float], mc_num: int = 100, seed: int = 0, device: int = 0) -> dict:
+    """``dist_ratios[i] = mean_j ||x_final(rej) - xr|| / mean_j ||x_final(no rej) - xr||`` for hold length i
+    (``disturbRejComp.py:85-98``).  Returns the ratios and both means; ``mc_num`` lanes per rank and setting."""
+    x0 = np.tile(np.asarray(sim_conditions.x0, float)[:, None], (1, mc_num))
+    nsteps = n_control_steps(sim_conditions)
+    rng = np.random.default_rng(seed + 7919 * _rank())
+    sig = np.asarray(noise_std, float)
+    means = np.zeros((len(noise_lengths), 2))
+    for i, nl in enumerate(noise_lengths):
+        R = noise_refreshes(nsteps, int(nl))
+        noise = rng.standard_normal((R, 2, mc_num)) * sig[None, :, None]
+        sums = np.zeros(4)
+        for k, rej in enumerate((False, True)):
+            sc = copy.copy(sim_conditions)
+            sc.isReject = rej
+            sc.noise = Noise(tuple(noise_std), int(nl))
+            run = _run(sc, mpc_params, fail_params, debris, x0, noise, device)
+            sums[2 * k] = run.stats["sum_final_dist"]
+            sums[2 * k + 1] = run.stats["n_lanes"]
+        sums = _allreduce_sum(sums, device)
+        means[i] = [sums[0] / sums[1], sums[2] / sums[3]]
+    return {"noise_lengths": np.asarray(noise_lengths, float), "mean_dist_norej": means[:, 0], "mean_dist_rej": means[:, 1],
+            "dist_ratios": means[:, 1] / means[:, 0]}
+
+
+def success_rate(sim_conditions, mpc_params, fail_params, debris, mc_num: int = 300, seed: int = 0, device: int = 0,
+                 x0_batch: Optional[np.ndarray] = None) -> dict:
+    """Fraction of successful approaches over ``mc_num`` noise realisations (``success_rates_test.py:66-75``)."""
+    x0 = np.tile(np.asarray(sim_conditions.x0, float)[:, None], (1, mc_num)) if x0_batch is None else np.ascontiguousarray(x0_batch.T)
+    nsteps = n_control_steps(sim_conditions)
+    noise = None
+    if sim_conditions.noise is not None:
+        rng = np.random.default_rng(seed + 7919 * _rank())
+        R = noise_refreshes(nsteps, int(sim_conditions.noise.noise_length))
+        noise = rng.standard_normal((R, 2, x0.shape[1])) * np.asarray(sim_conditions.noise.noise_std, float)[None, :, None]
+    run = _run(sim_conditions, mpc_params, fail_params, debris, x0, noise, device)
+    s = _allreduce_sum(np.array([run.stats["n_success"], run.stats["n_lanes"]]), device)
+    return {"success_count": int(s[0]), "runs": int(s[1]), "success_rate": s[0] / s[1]}

@@ -416,3 +416,29 @@ def test_debris_lanes_match_scalar_oracle(case, tol):
         np.testing.assert_allclose(got.ctrl_hist[:, :Tc + 1, b], r.ctrl_hist[:, :Tc + 1], rtol=0, atol=tol * U_ATOL)
         np.testing.assert_allclose(got.x_true[:, :Tc + 1, b], r.x_true[:, :Tc + 1], rtol=X_RTOL, atol=tol * X_ATOL)
         np.testing.assert_allclose(got.x_est[:, :Tc + 1, b], r.x_est[:, :Tc + 1], rtol=X_RTOL, atol=tol * X_ATOL)
+
+
+# ------------------------------------------------------------------------------------ Monte-Carlo drivers
+def test_monte_carlo_reductions_match_per_lane_results():
+    """disturbRejComp / success_rates_test as batched calls: the device-side statistics equal what the
+    per-lane outputs give, and rejection / no-rejection lanes share their noise realisation."""
+    case = dict(Nx=10, sigma=0.5, noise_length=10, T_final=20)
+    sc, mp, fp, _ = make_params(M, case)
+    out = M.final_distance_ratio_sweep(sc, mp, fp, None, (0.5, 0.5), [5., 20.], mc_num=24, seed=3)
+    assert out["dist_ratios"].shape == (2,) and np.all(np.isfinite(out["dist_ratios"]))
+    # recompute the first setting by hand through the batch API
+    rng = np.random.default_rng(3)
+    R = 40 // 5 + 1
+    noise = rng.standard_normal((R, 2, 24)) * 0.5
+    x0 = np.tile(np.asarray(sc.x0, float)[None, :], (24, 1))
+    means = []
+    for rej in (False, True):
+        sc.isReject = rej
+        sc.noise = M.Noise((0.5, 0.5), 5)
+        run = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
+        means.append(run.final_dist.mean())
+        assert run.stats["sum_final_dist"] == pytest.approx(run.final_dist.sum(), rel=1e-12)
+    assert out["dist_ratios"][0] == pytest.approx(means[1] / means[0], rel=1e-12)
+    sc.isReject = True
+    sr = M.success_rate(sc, mp, fp, None, mc_num=16, seed=1)
+    assert sr["runs"] == 16 and 0 <= sr["success_count"] <= 16
