@@ -15,6 +15,7 @@
 #include "sim.cuh"
 #include "team.cuh"
 #include "generic.cuh"
+#include "tile.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
@@ -102,6 +103,13 @@ struct mpcb_handle {
   size_t team_smem = 0;
   const void *team_fn_ptr = nullptr;
   int team_ctas = 0;
+  // tile kernel (DMMA, 8 lanes per warp): the round-based solver block for large batches of the n = 81 family
+  bool tile_ok = false;
+  TileHdr tile_hdr;
+  unsigned char *d_tile_blob[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t tile_smem = 0;
+  int tile_warps = 4;
+  int64_t tile_min_lanes = 16384;      // batches at least this large solve on the tile kernel (MPCB_SOLVER overrides)
   // per-lane path (debris lanes)
   bool generic_ok = false;
   GenArgs gproto;
@@ -315,12 +323,15 @@ static void set_warps(mpcb_handle *h, int w) {
 // slot at [(base + e) * TEAM + thread]), the sign-patch list, k-major V per variant.
 typedef void (*team_fn)(const TeamArgs);
 struct TeamShape { int n, m, wa, wat2, wp, ss; team_fn fn; };
-static const TeamShape kTeamShapes[] = {
-  {81, 136, 8, 6, 4, 8, team_kernel<81, 136, 8, 6, 4, 8>},     // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
+static const TeamShape kTeamShapes[] = {      // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
+  {81, 136, 8, 6, 4, 0, team_kernel<81, 136, 8, 6, 4, 0, true>},      // operator in tensor memory, A / A' rows in registers
+  {81, 136, 8, 6, 4, 8, team_kernel<81, 136, 8, 6, 4, 8, false>},     // operator in registers + 8 entries per thread in shared memory (MPCB_TEAM=regs)
 };
 static const TeamShape *team_shape_for(int n, int m) {
+  const char *e = getenv("MPCB_TEAM");
+  const bool regs = e && strcmp(e, "regs") == 0;
   for (const TeamShape &t : kTeamShapes)
-    if (t.n == n && t.m == m) return &t;
+    if (t.n == n && t.m == m && (t.ss != 0) == regs) return &t;
   return nullptr;
 }
 
@@ -517,6 +528,122 @@ static int launch_team(mpcb_handle *h, const TeamArgs &ta) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// Tile kernel tables (tile.cuh): V padded for the DMMA fragment patterns, byte-indexed ELL.
+static const int TILE_N = 81, TILE_M = 136, TILE_WARPS = 4, TILE_WA = 8, TILE_WAT = 11, TILE_WP = 4;
+static int build_tile_tables(mpcb_handle *h) {
+  const HostProblem &hp = h->hp;
+  const mpcb_problem &p = hp.p;
+  const int n = p.n, m = p.m;
+  if (n != TILE_N || m != TILE_M) return MPCB_OK;
+  const int ks = (n + 3) / 4, nt8 = (n + 7) / 8;
+  const int ldv = ((4 * ks - 4 + 15) / 16) * 16 + 4, ldm = ((m - 4 + 15) / 16) * 16 + 4;
+  const int nX = 4 * (p.Nx + 1);
+  TileHdr hd;
+  memset(&hd, 0, sizeof hd);
+  std::vector<std::vector<unsigned char>> blobs(4);
+  for (int v = 0; v < 4; ++v) {
+    std::vector<double> A;
+    variant_matrix(hp, v, A);
+    int off = 0;
+    auto take = [&](size_t bytes) {
+      const int o = off;
+      off = align16(off + (int)bytes);
+      return o;
+    };
+    TileHdr hv;
+    memset(&hv, 0, sizeof hv);
+    hv.off_V = take((size_t)8 * nt8 * 8 * ldv);
+    hv.off_lam = take(8 * ldv); hv.off_q = take(8 * ldv); hv.off_D = take(8 * ldv); hv.off_Dinv = take(8 * ldv);
+    hv.off_E = take(8 * ldm); hv.off_Einv = take(8 * ldm); hv.off_lt = take(8 * ldm); hv.off_ut = take(8 * ldm);
+    hv.off_Av = take((size_t)8 * TILE_WA * ldm); hv.off_ATv = take((size_t)8 * TILE_WAT * ldv); hv.off_Pv = take((size_t)8 * TILE_WP * ldv);
+    hv.off_Ac = take((size_t)TILE_WA * ldm); hv.off_ATc = take((size_t)TILE_WAT * ldv); hv.off_Pc = take((size_t)TILE_WP * ldv);
+    hv.off_An = take(ldm); hv.off_ATn = take(ldv); hv.off_Pn = take(ldv);
+    hv.off_flags = take(ldm); hv.off_pcode = take(ldm);
+    hv.total = off;
+    if (v == 0) hd = hv;
+    std::vector<unsigned char> &b = blobs[v];
+    b.assign(hv.total, 0);
+    double *Vd = reinterpret_cast<double *>(b.data() + hv.off_V);
+    const double *V = hp.V.data() + (size_t)v * n * n;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Vd[(size_t)i * ldv + j] = V[(size_t)i * n + j];
+    auto dv = [&](int o) { return reinterpret_cast<double *>(b.data() + o); };
+    for (int j = 0; j < n; ++j) {
+      dv(hv.off_lam)[j] = hp.lam[(size_t)v * n + j];
+      dv(hv.off_q)[j] = hp.q_s[j];
+      dv(hv.off_D)[j] = hp.D[j];
+      dv(hv.off_Dinv)[j] = 1.0 / hp.D[j];
+    }
+    for (int i = 0; i < m; ++i) {
+      dv(hv.off_E)[i] = hp.E[i];
+      dv(hv.off_Einv)[i] = 1.0 / hp.E[i];
+      dv(hv.off_lt)[i] = hp.l_s[i];
+      dv(hv.off_ut)[i] = hp.u_s[i];
+      unsigned char f = 0;
+      if (hp.l_s[i] < -1e30 * 1e-4) f |= 1;
+      if (hp.u_s[i] > 1e30 * 1e-4) f |= 2;
+      if (hp.ctype[i] == 1) f |= 4;
+      if (hp.ctype[i] == -1) f |= 8;
+      b[hv.off_flags + i] = f;
+      unsigned char pc = 0;
+      if (i < 4) pc = 1;
+      else if (i == m - 2) pc = 3;
+      else if (i == m - 1) pc = 4;
+      else if (i >= nX && i < nX + 5 * (p.Nb + 1) && (i - nX) % 5 == 3) pc = 2;
+      b[hv.off_pcode + i] = pc;
+      int k = 0;
+      for (int c = 0; c < n; ++c) {
+        const double val = A[(size_t)i * n + c];
+        if (val != 0.0) {
+          if (k >= TILE_WA) return MPCB_OK;
+          dv(hv.off_Av)[(size_t)k * ldm + i] = val;
+          b[hv.off_Ac + (size_t)k * ldm + i] = (unsigned char)c;
+          ++k;
+        }
+      }
+      b[hv.off_An + i] = (unsigned char)k;
+    }
+    for (int j = 0; j < n; ++j) {
+      int k = 0;
+      for (int i = 0; i < m; ++i) {
+        const double val = A[(size_t)i * n + j];
+        if (val != 0.0) {
+          if (k >= TILE_WAT) return MPCB_OK;
+          dv(hv.off_ATv)[(size_t)k * ldv + j] = val;
+          b[hv.off_ATc + (size_t)k * ldv + j] = (unsigned char)i;
+          ++k;
+        }
+      }
+      b[hv.off_ATn + j] = (unsigned char)k;
+      k = 0;
+      for (int c = 0; c < n; ++c) {
+        const double val = hp.P_s[(size_t)j * n + c];
+        if (val != 0.0) {
+          if (k >= TILE_WP) return MPCB_OK;
+          dv(hv.off_Pv)[(size_t)k * ldv + j] = val;
+          b[hv.off_Pc + (size_t)k * ldv + j] = (unsigned char)c;
+          ++k;
+        }
+      }
+      b[hv.off_Pn + j] = (unsigned char)k;
+    }
+  }
+  h->tile_warps = TILE_WARPS;
+  h->tile_smem = (size_t)hd.total + (size_t)TILE_WARPS * 8 * (ldv + 3 * ldm) * 8;
+  if (h->tile_smem > 227 * 1024) return MPCB_OK;
+  for (int v = 0; v < 4; ++v) {
+    CK(cudaMalloc(&h->d_tile_blob[v], hd.total));
+    CK(cudaMemcpy(h->d_tile_blob[v], blobs[v].data(), hd.total, cudaMemcpyHostToDevice));
+  }
+  CK(cudaFuncSetAttribute((const void *)admm_tile_kernel<TILE_N, TILE_M, TILE_WARPS, TILE_WA, TILE_WAT, TILE_WP>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
+  h->tile_hdr = hd;
+  h->tile_ok = true;
+  return MPCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-lane path tables: sparsity pattern of A (CSR + CSC view) with entry kinds, P in COO, unscaled vectors.
 template <typename Tv>
@@ -700,6 +827,7 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
     if (rc == MPCB_OK) {
       set_warps(h, h->warps);
       rc = build_team_tables(h);
+      if (rc == MPCB_OK) rc = build_tile_tables(h);
     }
   }
   if (rc != MPCB_OK) {
@@ -740,6 +868,7 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
   }
   cudaFree(h->d_tot);
   cudaFree(h->gen_scratch);
+  for (int v = 0; v < 4; ++v) cudaFree(h->d_tile_blob[v]);
   for (void *q : h->gen_bufs) cudaFree(q);
   for (StageBuf &b : h->stage_pool) cudaFree(b.ptr);
   cudaFree(h->d_tblob);
@@ -863,7 +992,23 @@ static void fill_args(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int mode) {
 
 // The lockstep round loop: every round runs one check_termination block of ADMM for all
 // still-solving lanes, then the per-lane epilogue for the lanes whose solve ended.
-static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf) {
+
+// Which solver block runs this batch.  MPCB_SOLVER = tile | team | block forces one; by default batches of at least
+// tile_min_lanes lanes go to the DMMA tile kernel (throughput), smaller ones to the persistent team kernel (latency).
+static bool want_tile(const mpcb_handle *h) {
+  if (!h->tile_ok) return false;
+  const char *e = getenv("MPCB_SOLVER");
+  if (e && *e) return strcmp(e, "tile") == 0;
+  return h->B >= h->tile_min_lanes;
+}
+static bool want_team(const mpcb_handle *h) {
+  if (!h->team_ok) return false;
+  const char *e = getenv("MPCB_SOLVER");
+  if (e && *e) return strcmp(e, "team") == 0;
+  return true;
+}
+
+static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false) {
   const int64_t B = h->B;
   const int W = h->warps;
   const int pgrid = (int)((B + 127) / 128);
@@ -895,7 +1040,24 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf)
       e1 = h->ev_pool[ev_used++];
       CK(cudaEventRecord(e0, h->stream));
     }
-    h->kern.fn<<<grid, 32 * W, h->smem_bytes, h->stream>>>(aa);
+    if (use_tile) {
+      TileArgs ta;
+      memset(&ta, 0, sizeof ta);
+      ta.hdr = h->tile_hdr;
+      for (int v = 0; v < 4; ++v) ta.blob[v] = h->d_tile_blob[v];
+      ta.n = aa.n; ta.m = aa.m; ta.uoff = aa.uoff; ta.B = aa.B;
+      ta.sigma = aa.sigma; ta.alpha = aa.alpha; ta.eps_abs = aa.eps_abs; ta.eps_rel = aa.eps_rel; ta.eps_pinf = aa.eps_pinf;
+      ta.adapt_tol = aa.adapt_tol; ta.cinv = aa.cinv; ta.qn_unscaled = aa.qn_unscaled; ta.qn_scaled = aa.qn_scaled;
+      ta.check_every = aa.check_every; ta.adaptive = aa.adaptive; ta.adapt_interval = aa.adapt_interval; ta.max_iter = aa.max_iter;
+      ta.cnt = aa.cnt; ta.list = aa.list; ta.xs = aa.xs; ta.zs = aa.zs; ta.ys = aa.ys; ta.rho = aa.rho; ta.iter = aa.iter;
+      ta.status = aa.status; ta.par = aa.par; ta.u0 = aa.u0; ta.lane_state = aa.lane_state; ta.flip = aa.flip;
+      ta.iter_total = aa.iter_total;
+      int tgrid = 0;
+      for (int v = 0; v < 4; ++v) tgrid += (h->h_cnt[v] + 8 * h->tile_warps - 1) / (8 * h->tile_warps);
+      admm_tile_kernel<TILE_N, TILE_M, TILE_WARPS, TILE_WA, TILE_WAT, TILE_WP><<<tgrid, 32 * TILE_WARPS, h->tile_smem, h->stream>>>(ta);
+    } else {
+      h->kern.fn<<<grid, 32 * W, h->smem_bytes, h->stream>>>(aa);
+    }
     if (h->timing) CK(cudaEventRecord(e1, h->stream));
     post_kernel<<<pgrid, 128, 0, h->stream>>>(pa);
     CK(cudaGetLastError());
@@ -1011,7 +1173,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
     g.xhat = d_xhat;
     g.warm = 1;
     RC(launch_generic(h, g));
-  } else if (h->team_ok) {
+  } else if (!want_tile(h) && want_team(h)) {
     TeamArgs ta;
     fill_team_args(h, ta, MODE_QP_ONLY);
     ta.xhat = d_xhat;
@@ -1024,7 +1186,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
     pa.list_next = h->list;
     qp_prepare_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_xhat);
     h->ctr.kernel_launches += 1;
-    RC(run_rounds(h, aa, pa, 0));
+    RC(run_rounds(h, aa, pa, 0, want_tile(h)));
   }
   if (d_u0) CK(cudaMemcpyAsync(d_u0, h->u0, (size_t)2 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
   if (d_st || d_it) {
@@ -1183,7 +1345,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     g.n_refresh = n_refresh;
     g.warm = 0;
     RC(launch_generic(h, g));
-  } else if (h->team_ok && mode == MODE_DISCRETE) {
+  } else if (!want_tile(h) && want_team(h) && mode == MODE_DISCRETE) {
     TeamArgs ta;
     fill_team_args(h, ta, MODE_DISCRETE);
     ta.nsteps = nsteps;
@@ -1201,7 +1363,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;
-    RC(run_rounds(h, aa, pa, 0));
+    RC(run_rounds(h, aa, pa, 0, want_tile(h)));
     finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;

@@ -454,11 +454,66 @@ __device__ __forceinline__ double ell_dot(const double *vals, int stride, const 
   return acc0 + acc1;
 }
 
+
+// W entries of one ELL row whose values / packed column indices already sit in registers (tensor-memory mode).
+template <int W, int WMAX>
+__device__ __forceinline__ double ell_dot_reg(const double (&v)[WMAX], const uint4 &c, const double *vec) {
+  const unsigned cw[4] = {c.x, c.y, c.z, c.w};
+  double g[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e) g[e] = vec[(e & 1) ? (cw[e >> 1] >> 16) : (cw[e >> 1] & 0xffffu)];
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    if (e & 1) acc1 = fma(v[e], g[e], acc1);
+    else acc0 = fma(v[e], g[e], acc0);
+  }
+  return acc0 + acc1;
+}
+
+// ---- tensor memory as per-thread operand storage: shape 32x32b, thread t of a warp <-> TMEM lane 32*(warp%4)+t,
+//      consecutive 32-bit columns <-> consecutive registers.  The per-lane operator S lives here in TM mode.
+#define TMEM_LD_REGS16(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+#define TMEM_ST_REGS16(r) "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+                          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : TMEM_LD_REGS16(r) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), TMEM_ST_REGS16(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// The waits name the registers the pending loads write ("+r"): the compiler must not move a read of them above the wait.
+#define TMEM_RW_REGS16(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
+                          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+__device__ __forceinline__ void tmem_wait_ld2(uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TMEM_RW_REGS16(r), TMEM_RW_REGS16(q) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+
 // ------------------------------------------------------------------------------------------
 // N variables, M rows (M <= 256, 2N <= 256); WA (<= 8), WAT2 (<= 8, entry PAIRS), WP are the maximum
 // ELL widths the instantiation supports.  Of the HALF entries of S a thread owns, the last SS live in
 // shared memory ([SS][NCT], conflict-free) and the rest in registers.
-template <int N, int M, int WA, int WAT2, int WP, int SS>
+//
+// TM (tensor-memory mode): the whole of S lives in TMEM (2*HALF 32-bit columns per thread, 256 columns per CTA, two
+// CTAs per SM = all 512), read back chunk by chunk with tcgen05.ld in the mat-vec.  The LSU data pipe -- not FP64
+// -- is what two teams per SM saturate (tools/ubench_tmem.cu, ubench_lds.cu: every LDS.64 a warp issues costs
+// the pipe a cycle, broadcast or not), so in this mode the registers S vacated hold the thread's rows of A / A'
+// (values and packed column indices), which removes the table loads from every iteration, and SS must be 0.
+template <int N, int M, int WA, int WAT2, int WP, int SS, bool TM>
 __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __grid_constant__ TeamArgs a) {
   constexpr int TEAM = TEAM_THREADS;
   constexpr int HALF = ((N + 3) / 4) * 2;  // entries of a row of S per thread (even); 2*HALF >= N
@@ -468,6 +523,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   constexpr int NCT = ((2 * N + 31) / 32) * 32;   // threads that run the pair phases: whole warps (shuffles stay convergent)
   constexpr int SR = HALF - SS;            // entries of S per thread kept in registers
   static_assert(SS % 2 == 0 && SR % 2 == 0 && SR > 0, "S split must be even");
+  static_assert(!TM || (SS == 0 && HALF > 32 && HALF <= 48 && HALF % 2 == 0 && TEAM <= 256), "tensor-memory mode: 2*HALF columns per thread, two warps per lane quarter");
   static_assert(2 * N <= TEAM && M <= TEAM && WA <= 8 && WAT2 <= 8, "team too small");
   extern __shared__ __align__(128) unsigned char smem[];
   const TeamHdr &h = a.hdr;
@@ -495,7 +551,18 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   if (tid < 12) ukf.Bou[tid] = a.sc.Bou[tid];
   if (tid == 0) ukf.dbg = a.tot;
   for (int o = tid; o < SS * NCT; o += TEAM) Ssm[o] = 0.0;
+  __shared__ uint32_t s_tmem;
+  if (TM) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+  }
   __syncthreads();
+  if (TM) asm volatile("tcgen05.fence::after_thread_sync;");
+  // this thread's 2*HALF columns: lane quarter warp%4, the upper four warps sit beside the lower four
+  const uint32_t taddr = TM ? s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(2 * HALF * (warp >> 2)) : 0u;
 
   const double *qv = reinterpret_cast<const double *>(smem + h.off_q);
   const double *Dv = reinterpret_cast<const double *>(smem + h.off_D);
@@ -524,7 +591,34 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   const double sigma = a.sigma, alpha = a.alpha, oma = 1.0 - a.alpha;
 
   // A warp-uniform switch picks a fully unrolled body, so every load of a phase is in flight at once.
+  // tensor-memory mode: this thread's row of A and half-column of A' in registers (reloaded when the sign variant changes)
+  double Ar[TM ? WA : 1], ATr[TM ? WAT2 : 1];
+  uint4 Acr = make_uint4(0, 0, 0, 0), ATcr = make_uint4(0, 0, 0, 0);
+  auto load_tables = [&]() {
+    if constexpr (TM) {
+#pragma unroll
+      for (int e = 0; e < WA; ++e) Ar[e] = has_row ? Avals[e * MP + tid] : 0.0;
+#pragma unroll
+      for (int e = 0; e < WAT2; ++e) ATr[e] = col_warp ? ATvals[e * NCT + tid] : 0.0;
+      if (has_row) Acr = Acols[tid];
+      if (col_warp) ATcr = ATcols[tid];
+    }
+  };
+  load_tables();
   auto applyA = [&](const double *vec) -> double {          // row `row` of A times vec (thread tid < M)
+    if constexpr (TM) {
+      switch (wA) {
+        case 1: return ell_dot_reg<1>(Ar, Acr, vec);
+        case 2: return ell_dot_reg<2>(Ar, Acr, vec);
+        case 3: return ell_dot_reg<3>(Ar, Acr, vec);
+        case 4: return ell_dot_reg<4>(Ar, Acr, vec);
+        case 5: return ell_dot_reg<5>(Ar, Acr, vec);
+        case 6: return ell_dot_reg<6>(Ar, Acr, vec);
+        case 7: return ell_dot_reg<(WA >= 7 ? 7 : WA)>(Ar, Acr, vec);
+        case 8: return ell_dot_reg<(WA >= 8 ? 8 : WA)>(Ar, Acr, vec);
+        default: return 0.0;
+      }
+    }
     const uint4 c = Acols[tid];
     const double *v = Avals + tid;
     switch (wA) {
@@ -543,6 +637,20 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
     const uint4 c = ATcols[tid];
     const double *v = ATvals + tid;
     double acc;
+    if constexpr (TM) {
+      switch (wAT2) {
+        case 1: acc = ell_dot_reg<1>(ATr, ATcr, vec); break;
+        case 2: acc = ell_dot_reg<2>(ATr, ATcr, vec); break;
+        case 3: acc = ell_dot_reg<3>(ATr, ATcr, vec); break;
+        case 4: acc = ell_dot_reg<4>(ATr, ATcr, vec); break;
+        case 5: acc = ell_dot_reg<(WAT2 >= 5 ? 5 : WAT2)>(ATr, ATcr, vec); break;
+        case 6: acc = ell_dot_reg<(WAT2 >= 6 ? 6 : WAT2)>(ATr, ATcr, vec); break;
+        case 7: acc = ell_dot_reg<(WAT2 >= 7 ? 7 : WAT2)>(ATr, ATcr, vec); break;
+        case 8: acc = ell_dot_reg<(WAT2 >= 8 ? 8 : WAT2)>(ATr, ATcr, vec); break;
+        default: acc = 0.0; break;
+      }
+      return acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+    }
     switch (wAT2) {
       case 1: acc = ell_dot<1>(v, NCT, c, vec); break;
       case 2: acc = ell_dot<2>(v, NCT, c, vec); break;
@@ -633,16 +741,64 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         }
       }
       int iter = 0, st = -10;
-      bool need_op = (variant != op_variant) || (rho != op_rho);
+      const bool resigned = variant != op_variant;
+      bool need_op = resigned || (rho != op_rho);
       op_variant = variant;
       const uint8_t fl = has_row ? flags[row] : (uint8_t)8;
       __syncthreads();
+      if (TM && resigned) load_tables();
 
       // =============================== one solve ===============================
       while (st == -10) {
         if (need_op) {                   // S = V diag(1/(1+rho*lam)) V'
           if (tid < N) dk[tid] = 1.0 / (1.0 + rho * a.lam[variant * N + tid]);
           __syncthreads();
+          if constexpr (TM) {
+            // three passes over V (16 + 16 + (HALF-32) entries of this thread's half row) keep the accumulators small;
+            // the summation order over k is the register version's, so S is bit-identical to it
+            if (col_warp) {
+              const double *Vk = a.Vk[variant];
+#pragma unroll 1
+              for (int pass = 0; pass < 3; ++pass) {
+                double T[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) T[j] = 0.0;
+                const int cnt2 = (pass < 2) ? 8 : (HALF - 32) / 2;
+                for (int k = 0; k < N; ++k) {
+                  const double *vrow = Vk + (size_t)k * NP2;
+                  const double tk = has_col ? __ldg(vrow + col) * dk[k] : 0.0;
+                  const double2 *r2 = reinterpret_cast<const double2 *>(vrow + half * HALF + 16 * pass);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (j < cnt2) {
+                      const double2 vv = __ldg(r2 + j);
+                      T[2 * j] = fma(tk, vv.x, T[2 * j]);
+                      T[2 * j + 1] = fma(tk, vv.y, T[2 * j + 1]);
+                    }
+                }
+                uint32_t w[16];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    w[2 * j] = (uint32_t)__double2loint(T[8 * hh + j]);
+                    w[2 * j + 1] = (uint32_t)__double2hiint(T[8 * hh + j]);
+                  }
+                  const int c0 = 32 * pass + 16 * hh;               // first column of these 8 doubles
+                  if (c0 + 16 <= 2 * HALF) tmem_st16(taddr + c0, w);
+                  else if (c0 < 2 * HALF) {                          // tail: 2*HALF - c0 columns, in 4-column pieces
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                      if (c0 + 4 * q < 2 * HALF) {
+                        const uint32_t w4[4] = {w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]};
+                        tmem_st4(taddr + c0 + 4 * q, w4);
+                      }
+                  }
+                }
+              }
+              tmem_wait_st();
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < SR; ++j) S[j] = 0.0;
           if (has_col) {
@@ -670,6 +826,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
 #pragma unroll
             for (int j = 0; j < SS; ++j) Ssm[j * NCT + tid] = T[j];
           }
+          }
           op_rho = rho;
           need_op = false;
           ++my_rebuilds;
@@ -689,7 +846,56 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             if (has_col && half == 0) rbuf[col] = sigma * x - qv[col] + s;
           }
           __syncthreads();
-          if (col_warp) {
+          if (TM && col_warp) {
+            // S streams out of tensor memory in 16-column chunks (8 doubles), two chunks in flight
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
+            uint32_t ca[16], cb[16];
+            auto use = [&](const uint32_t (&c)[16], int q) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const double2 rr = r2[4 * q + j];
+                const double s0 = u2d(c[4 * j], c[4 * j + 1]), s1 = u2d(c[4 * j + 2], c[4 * j + 3]);
+                if (j & 1) {
+                  a2 = fma(s0, rr.x, a2);
+                  a3 = fma(s1, rr.y, a3);
+                } else {
+                  a0 = fma(s0, rr.x, a0);
+                  a1 = fma(s1, rr.y, a1);
+                }
+              }
+            };
+            constexpr int NCH = (2 * HALF) / 16;       // full chunks; the remaining (2*HALF - 16*NCH) / 4 doubles pairs come as x4 loads
+            tmem_ld16(taddr, ca);
+            tmem_ld16(taddr + 16, cb);
+            tmem_wait_ld2(ca, cb);
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              if (q & 1) {
+                use(cb, q);
+                if (q + 2 < NCH) tmem_ld16(taddr + 16 * (q + 2), cb);
+              } else {
+                use(ca, q);
+                if (q + 2 < NCH) tmem_ld16(taddr + 16 * (q + 2), ca);
+              }
+              if ((q & 1) && q + 1 < NCH) tmem_wait_ld2(ca, cb);
+              if (!(q & 1) && q + 1 < NCH && q + 2 >= NCH) tmem_wait_ld2(ca, cb);
+            }
+#pragma unroll
+            for (int c0 = 16 * NCH; c0 < 2 * HALF; c0 += 4) {
+              uint32_t c4[4];
+              tmem_ld4(taddr + c0, c4);
+              tmem_wait_ld4(c4);
+              const double2 rr = r2[c0 / 4];
+              a0 = fma(u2d(c4[0], c4[1]), rr.x, a0);
+              a1 = fma(u2d(c4[2], c4[3]), rr.y, a1);
+            }
+            double xt = (a0 + a1) + (a2 + a3);
+            xt += __shfl_xor_sync(0xffffffffu, xt, 1);
+            if (has_col && half == 0) xtbuf[col] = xt;
+            x = alpha * xt + oma * x;
+          }
+          if (!TM && col_warp) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
 #pragma unroll
@@ -850,6 +1056,10 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
     if (tid == 0) lane_finalize(a, L);
   }
   TP_FLUSH
+  if (TM) {
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(s_tmem));
+  }
   if (tid == 0) {
     if (my_iters) atomicAdd(&a.tot[0], my_iters);
     if (my_rebuilds) atomicAdd(&a.tot[2], my_rebuilds);

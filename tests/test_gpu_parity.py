@@ -35,9 +35,21 @@ def lanes(case, B, seed):
 @pytest.mark.parametrize("Nx", [10, 20, 30, 40])
 def test_qp_solve_cold_and_warm(Nx):
     """mpcb_qp_solve == prob.update(l,u); prob.update(Ax,l,u); prob.solve() lane by lane."""
+    _qp_seam(Nx, 48)
+
+
+@pytest.mark.parametrize("solver,B", [("tile", 48), ("tile", 77), ("block", 48), ("team", 48)])
+def test_qp_solve_every_solver_block(solver, B, monkeypatch):
+    """The same seam with each of the three solver blocks forced (MPCB_SOLVER): the DMMA tile kernel
+    (8 lanes per warp; B = 77 leaves ragged tiles in every sign variant), the warp-per-lane block
+    kernel and the persistent team kernel all reproduce the oracle's iterates."""
+    monkeypatch.setenv("MPCB_SOLVER", solver)
+    _qp_seam(10, B)
+
+
+def _qp_seam(Nx, B):
     case = dict(Nx=Nx, sigma=0.1)
     sc, mp, fp, _ = make_params(M, case)
-    B = 48
     rng = np.random.default_rng(Nx)
     s = build_setup(sc, mp, fp, None)
     qp = BatchedQP(s, B)
@@ -157,6 +169,18 @@ def _compare_batch(got, ref, B):
 
 @pytest.mark.parametrize("name", list(DISCRETE))
 def test_discrete_closed_loop_matches_batched_oracle(name):
+    _closed_loop(name)
+
+
+@pytest.mark.parametrize("solver", ["tile", "block"])
+def test_discrete_closed_loop_every_solver_block(solver, monkeypatch):
+    monkeypatch.setenv("MPCB_SOLVER", solver)
+    for name, (case, _) in DISCRETE.items():
+        if case.get('Nx', 10) == 10:
+            _closed_loop(name)
+
+
+def _closed_loop(name):
     case, B = DISCRETE[name]
     x0, rng = lanes(case, B, 11)
     sc, mp, fp, _ = make_params(M, case)
