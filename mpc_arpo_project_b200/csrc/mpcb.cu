@@ -100,6 +100,11 @@ struct mpcb_handle {
   double *d_Vk[4] = {nullptr, nullptr, nullptr, nullptr};
   double *d_lam = nullptr;
   int *d_queue = nullptr;
+  // per-lane operator cache of the tensor-memory team kernel (list mode), allocated on first use
+  double *scache = nullptr, *scache_rho = nullptr;
+  int *scache_var = nullptr;
+  bool scache_tried = false, team_tm = false;
+  int visit_iters = -1;                // list mode: iterations per lane visit; -1 = sized per round, 0 = unlimited (MPCB_VISIT_ITERS)
   size_t team_smem = 0;
   const void *team_fn_ptr = nullptr;
   int team_ctas = 0;
@@ -109,7 +114,7 @@ struct mpcb_handle {
   unsigned char *d_tile_blob[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t tile_smem = 0;
   int tile_warps = 4;
-  int64_t tile_min_lanes = 16384;      // batches at least this large solve on the tile kernel (MPCB_SOLVER overrides)
+  int64_t tile_min_lanes = INT64_MAX;  // the tile kernel is opt-in (MPCB_SOLVER=tile): the team kernel is faster at every batch size measured so far
   // per-lane path (debris lanes)
   bool generic_ok = false;
   GenArgs gproto;
@@ -470,6 +475,7 @@ static int build_team_tables(mpcb_handle *h) {
   h->team_smem = (size_t)hd.total + 8 * (size_t)(5 * mp + 3 * np2 + 16 * nw + ts->ss * nct) + ((sizeof(UkfScratch) + 15) & ~15) +
                  sizeof(LaneCtx) + 16;
   h->team_ctas = TEAM_CTAS;
+  h->team_tm = ts->ss == 0;
   h->team_fn_ptr = (const void *)ts->fn;
   CK(cudaFuncSetAttribute(h->team_fn_ptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->team_smem));
   h->team_ok = true;
@@ -848,6 +854,8 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
 }
 
 static void free_batch(mpcb_handle *h) {
+  cudaFree(h->scache); cudaFree(h->scache_rho); cudaFree(h->scache_var);
+  h->scache = h->scache_rho = nullptr; h->scache_var = nullptr; h->scache_tried = false;
   cudaFree(h->xs); cudaFree(h->zs); cudaFree(h->ys); cudaFree(h->rho); cudaFree(h->par); cudaFree(h->u0);
   cudaFree(h->iter); cudaFree(h->status); cudaFree(h->flip); cudaFree(h->lane_state); cudaFree(h->cnt);
   cudaFree(h->list); cudaFree(h->lane_f64); cudaFree(h->lane_i32);
@@ -993,8 +1001,8 @@ static void fill_args(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int mode) {
 // The lockstep round loop: every round runs one check_termination block of ADMM for all
 // still-solving lanes, then the per-lane epilogue for the lanes whose solve ended.
 
-// Which solver block runs this batch.  MPCB_SOLVER = tile | team | block forces one; by default batches of at least
-// tile_min_lanes lanes go to the DMMA tile kernel (throughput), smaller ones to the persistent team kernel (latency).
+// Which solver block runs this batch.  MPCB_SOLVER = tile | team | block forces one; the default is the persistent team
+// kernel where an instantiation exists (n = 81), else the warp-per-lane block kernel.
 static bool want_tile(const mpcb_handle *h) {
   if (!h->tile_ok) return false;
   const char *e = getenv("MPCB_SOLVER");
@@ -1010,6 +1018,27 @@ static bool want_team(const mpcb_handle *h) {
 
 static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false) {
   const int64_t B = h->B;
+  // n = 81 family: each round solves its lanes to completion on the team kernel (list mode) instead of advancing them
+  // check_termination iterations at a time; rounds then coincide with control steps
+  const bool use_team = !use_tile && want_team(h);
+  if (const char *e = getenv("MPCB_VISIT_ITERS")) h->visit_iters = std::max(-1, atoi(e));
+  if (use_team && h->team_tm && !h->scache_tried) {
+    h->scache_tried = true;
+    const size_t per_lane = (size_t)(((h->hp.p.n + 3) / 4)) * (((2 * h->hp.p.n + 31) / 32) * 32) * 16;
+    const char *e = getenv("MPCB_SCACHE_GB");
+    const double cap = (e && *e) ? atof(e) : 24.0;
+    if ((double)per_lane * (double)B <= cap * 1073741824.0) {
+      if (cudaMalloc(&h->scache, per_lane * (size_t)B) == cudaSuccess && cudaMalloc(&h->scache_rho, (size_t)B * 8) == cudaSuccess &&
+          cudaMalloc(&h->scache_var, (size_t)B * 4) == cudaSuccess) {
+        CK(cudaMemsetAsync(h->scache_rho, 0xff, (size_t)B * 8, h->stream));      // NaN tags: every slot empty
+        CK(cudaMemsetAsync(h->scache_var, 0xff, (size_t)B * 4, h->stream));
+      } else {
+        cudaGetLastError();
+        cudaFree(h->scache); cudaFree(h->scache_rho); cudaFree(h->scache_var);
+        h->scache = h->scache_rho = nullptr; h->scache_var = nullptr;
+      }
+    }
+  }
   const int W = h->warps;
   const int pgrid = (int)((B + 127) / 128);
   int cur = first_buf;
@@ -1040,7 +1069,22 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       e1 = h->ev_pool[ev_used++];
       CK(cudaEventRecord(e0, h->stream));
     }
-    if (use_tile) {
+    if (use_team) {
+      TeamArgs ta;
+      fill_team_args(h, ta, MODE_QP_ONLY);
+      ta.warm = 1;
+      ta.cnt = aa.cnt; ta.list = aa.list; ta.par = aa.par; ta.lane_state = aa.lane_state;
+      ta.scache = h->scache; ta.scache_rho = h->scache_rho; ta.scache_var = h->scache_var;
+      // Visit budget: a round lasts as long as its longest visit, so cap a visit at about the work an average CTA has
+      // this round (live/grid lanes x ~46 iterations); with a CTA per live lane nobody queues and solves run to completion.
+      const long cta_max = (long)h->num_sms * h->team_ctas;
+      if (h->visit_iters >= 0) ta.visit_iters = h->visit_iters;
+      else if (live <= cta_max) ta.visit_iters = 0;
+      else ta.visit_iters = (int)std::max<long>(4L * aa.check_every, (live / 10 / aa.check_every) * aa.check_every);
+      CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+      const int tgrid = (int)std::min<long>(live, (long)h->num_sms * h->team_ctas);
+      ((team_fn)h->team_fn_ptr)<<<tgrid, TEAM_THREADS, h->team_smem, h->stream>>>(ta);
+    } else if (use_tile) {
       TileArgs ta;
       memset(&ta, 0, sizeof ta);
       ta.hdr = h->tile_hdr;

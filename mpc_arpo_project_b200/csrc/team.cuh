@@ -100,6 +100,19 @@ struct TeamArgs {
   double *u0;                // [2][B]
   int *iter, *status, *flip;
   int warm;                  // 1: load x,z,y,rho from global (QP seam), 0: cold start
+  // list mode (MODE_QP_ONLY with list != nullptr): the round-based simulators' contract (admm.cuh) -- solve every lane
+  // of this round's per-variant lists to completion; parameters come from par, the verdict goes to lane_state
+  const int *cnt;            // [4] lanes per sign variant
+  const int *list;           // [4][B]
+  const double *par;         // [7][B]
+  uint8_t *lane_state;       // [B]
+  int visit_iters;           // > 0: at most this many iterations per visit; an unfinished lane keeps status -10 and stays listed,
+                             //      so one 4000-iteration solve does not hold up a round of 25..100-iteration ones
+  // per-lane operator cache (tensor-memory kernels): S of the lane's last solve, tagged with (rho, variant), so that a lane
+  // revisited every control step reloads 64 KB from HBM instead of redoing the n^3 rebuild
+  double *scache;            // [B][SCACHE_CHUNKS][NCT] double2, or nullptr
+  double *scache_rho;        // [B] rho the cached S was built for (< 0: empty)
+  int *scache_var;           // [B]
   // results
   int *queue;                // [1] next lane
   unsigned long long *tot;   // [0] admm iterations, [1] qp solves, [2] operator rebuilds
@@ -110,6 +123,8 @@ struct LaneCtx {
   double xtrue[4], ux[6], uP[36], xstore[4], unext[2], noise[2], xfin[4], par[7], u0[2];
   double xintf, rho;
   int step, iterm, succ, nsolve, variant, ukf_clamp, flip, fin, status, iter, lane;
+  double c_rho;              // operator-cache tag of this lane
+  int c_var;
 };
 
 struct UkfScratch {
@@ -368,11 +383,20 @@ __device__ __noinline__ void lane_init(const TeamArgs &a, LaneCtx &L, int ln) {
   L.xintf = 0.0;
   L.step = 0; L.succ = 0; L.nsolve = 0; L.ukf_clamp = 0; L.flip = 0; L.fin = 0; L.status = -10; L.iter = 0;
   L.u0[0] = L.u0[1] = 0.0;
+  L.c_rho = -1.0;
+  L.c_var = -1;
   if (a.mode == MODE_QP_ONLY) {
-    double xe[6];
-    for (int k = 0; k < 6; ++k) xe[k] = a.xhat[k * B + ln];
-    L.variant = ctx_params(c, L, xe);
-    if (a.warm) L.rho = a.rho[ln];
+    if (a.list) {            // variant was set by the caller (it comes with the list the lane was drawn from)
+      for (int k = 0; k < 7; ++k) L.par[k] = a.par[k * B + ln];
+      L.rho = a.rho[ln];
+      L.iter = a.iter[ln];
+      if (a.scache) { L.c_rho = a.scache_rho[ln]; L.c_var = a.scache_var[ln]; }
+    } else {
+      double xe[6];
+      for (int k = 0; k < 6; ++k) xe[k] = a.xhat[k * B + ln];
+      L.variant = ctx_params(c, L, xe);
+      if (a.warm) L.rho = a.rho[ln];
+    }
     L.iterm = 0;
     return;
   }
@@ -408,7 +432,12 @@ __device__ __noinline__ void lane_finalize(const TeamArgs &a, LaneCtx &L) {
     a.u0[(size_t)a.B + ln] = L.u0[1];
     a.rho[ln] = L.rho;
     if (L.flip) a.flip[ln] = 1;
-    atomicAdd(&a.tot[1], 1ull);
+    if (a.list) {
+      if (L.status != -10) a.lane_state[ln] = LANE_SOLVE_DONE;
+      if (a.scache) { a.scache_rho[ln] = L.c_rho; a.scache_var[ln] = L.c_var; }
+    } else {
+      atomicAdd(&a.tot[1], 1ull);
+    }
     return;
   }
   double d2 = 0.0;
@@ -496,6 +525,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
                           "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
 __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&r)[16], uint32_t (&q)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : TMEM_RW_REGS16(r), TMEM_RW_REGS16(q) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld1(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TMEM_RW_REGS16(r) :: "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld4(uint32_t (&r)[4]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
@@ -691,12 +723,32 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
 
   double S[SR];                          // S[col][half*HALF .. half*HALF+SR); the next SS entries are in Ssm[.][tid]
   int op_variant = 0;                    // sign variant baked into Avals / ATvals (blob = variant 0)
+  double op_rho = -1.0;                  // (rho, variant) the operator S currently held was built for: S depends on nothing
+  int s_variant = -1;                    // else, so it survives from one lane to the next when both match
+  constexpr int SCHUNKS = HALF / 2;      // double2 chunks of S per thread (operator cache layout [chunk][thread])
   unsigned long long my_iters = 0, my_rebuilds = 0;
   TP_DECL
 
   while (true) {
     __syncthreads();
-    if (tid == 0) s_lane = atomicAdd(a.queue, 1);
+    if (tid == 0) {
+      int q = atomicAdd(a.queue, 1);
+      if (a.list) {                      // q-th entry of the concatenated per-variant lists
+        int v = 0;
+        for (; v < 4; ++v) {
+          const int c = a.cnt[v];
+          if (q < c) break;
+          q -= c;
+        }
+        if (v < 4) {
+          q = a.list[(size_t)v * a.B + q];
+          L.variant = v;
+        } else {
+          q = a.B;
+        }
+      }
+      s_lane = q;
+    }
     __syncthreads();
     const int ln = s_lane;
     if (ln >= a.B) break;
@@ -710,8 +762,34 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         y = a.ys[(size_t)ln * M + row];
       }
     }
-    double op_rho = -1.0;                // rho the registers' S was built for (new lane: force a rebuild)
     __syncthreads();
+    if (TM && a.scache && (L.rho != op_rho || L.variant != s_variant) && L.c_rho == L.rho && L.c_var == L.variant) {
+      // this lane's operator is in its cache slot: HBM -> registers -> tensor memory
+      if (col_warp) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid;
+#pragma unroll
+        for (int g = 0; g < (2 * HALF) / 16; ++g) {
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 v = __ldcs(src + (size_t)(4 * g + j) * NCT);
+            w[4 * j] = (uint32_t)__double2loint(v.x); w[4 * j + 1] = (uint32_t)__double2hiint(v.x);
+            w[4 * j + 2] = (uint32_t)__double2loint(v.y); w[4 * j + 3] = (uint32_t)__double2hiint(v.y);
+          }
+          tmem_st16(taddr + 16 * g, w);
+        }
+#pragma unroll
+        for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
+          const double2 v = __ldcs(src + (size_t)c * NCT);
+          const uint32_t w4[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y),
+                                  (uint32_t)__double2hiint(v.y)};
+          tmem_st4(taddr + 4 * c, w4);
+        }
+        tmem_wait_st();
+      }
+      op_rho = L.rho;
+      s_variant = L.variant;
+    }
     TP_MARK(4)
 
     // =============================== control steps ===============================
@@ -740,9 +818,10 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
           }
         }
       }
-      int iter = 0, st = -10;
+      int iter = a.list ? L.iter : 0, st = -10;        // list mode: a solve may span several visits
+      int visit_left = a.visit_iters;
       const bool resigned = variant != op_variant;
-      bool need_op = resigned || (rho != op_rho);
+      bool need_op = (variant != s_variant) || (rho != op_rho);
       op_variant = variant;
       const uint8_t fl = has_row ? flags[row] : (uint8_t)8;
       __syncthreads();
@@ -828,6 +907,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
           }
           }
           op_rho = rho;
+          s_variant = variant;
           need_op = false;
           ++my_rebuilds;
           TP_MARK(2)
@@ -1028,6 +1108,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         }
         __syncthreads();                 // red / vbuf reads of this check are done before the next block writes
         TP_MARK(1)
+        if (a.visit_iters > 0 && (visit_left -= a.check_every) <= 0) break;     // visit budget spent: the lane is re-listed
       }  // solve
 
       // ---- hand the result to the lane context, run the rest of the control step on warp 0
@@ -1047,6 +1128,32 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
       TP_MARK(3)
     }  // control steps
 
+    // ---- list mode: leave the operator in the lane's cache slot unless the slot already holds it
+    if constexpr (TM) {
+      const bool put = a.list && a.scache && op_rho >= 0.0 && (L.c_rho != op_rho || L.c_var != s_variant);
+      __syncthreads();
+      if (put) {
+        if (col_warp) {
+          double2 *dst = reinterpret_cast<double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid;
+#pragma unroll
+          for (int g = 0; g < (2 * HALF) / 16; ++g) {
+            uint32_t w[16];
+            tmem_ld16(taddr + 16 * g, w);
+            tmem_wait_ld1(w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcs(dst + (size_t)(4 * g + j) * NCT, make_double2(u2d(w[4 * j], w[4 * j + 1]), u2d(w[4 * j + 2], w[4 * j + 3])));
+          }
+#pragma unroll
+          for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
+            uint32_t w4[4];
+            tmem_ld4(taddr + 4 * c, w4);
+            tmem_wait_ld4(w4);
+            __stcs(dst + (size_t)c * NCT, make_double2(u2d(w4[0], w4[1]), u2d(w4[2], w4[3])));
+          }
+        }
+        if (tid == 0) { L.c_rho = op_rho; L.c_var = s_variant; }
+      }
+    }
     // ---- lane done: persist solver iterates (QP seam warm start / mpcb_qp_get_state), final results
     if (has_col && half == 0) a.xs[(size_t)ln * N + col] = x;
     if (has_row) {
