@@ -308,13 +308,17 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize(dev)
             tot_ms += e0.elapsed_time(e1)
+            if os.environ.get("BENCH_VERBOSE"):
+                print(f"[bench] step {e0.elapsed_time(e1):.2f} ms", file=sys.stderr)
             solves += int(res.stats["qp_solves"])
         return tot_ms, solves, res
 
+    # the sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML init, ~0.3 s) stalls the GPU it queries and
+    # would otherwise inflate one of the first timed steps by 20-30 ms; its steady 100 ms polling does not show
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     for _ in range(args.warmup):
         step(True)
     c0 = eng.counters()
-    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
     sync_all()
     ms, solves, res = timed(args.steps, True)
     sync_all()

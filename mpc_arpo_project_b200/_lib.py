@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmpcb.so")
+# MPCB_LIB: load another build of the same ABI (A/B timing of kernel variants on one box); default is the in-tree library
+LIB_PATH = os.environ.get("MPCB_LIB") or os.path.join(_HERE, "lib", "libmpcb.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -639,17 +639,11 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   load_tables();
   auto applyA = [&](const double *vec) -> double {          // row `row` of A times vec (thread tid < M)
     if constexpr (TM) {
-      switch (wA) {
-        case 1: return ell_dot_reg<1>(Ar, Acr, vec);
-        case 2: return ell_dot_reg<2>(Ar, Acr, vec);
-        case 3: return ell_dot_reg<3>(Ar, Acr, vec);
-        case 4: return ell_dot_reg<4>(Ar, Acr, vec);
-        case 5: return ell_dot_reg<5>(Ar, Acr, vec);
-        case 6: return ell_dot_reg<6>(Ar, Acr, vec);
-        case 7: return ell_dot_reg<(WA >= 7 ? 7 : WA)>(Ar, Acr, vec);
-        case 8: return ell_dot_reg<(WA >= 8 ? 8 : WA)>(Ar, Acr, vec);
-        default: return 0.0;
-      }
+      // values and indices are registers: padding a row to its class width costs one broadcast load and one FMA per
+      // pad, a jump table (LDC + BRX, on the critical path of every iteration) costs more
+      if (wA > 5) return ell_dot_reg<WA>(Ar, Acr, vec);
+      if (wA > 2) return ell_dot_reg<(WA >= 5 ? 5 : WA)>(Ar, Acr, vec);
+      return ell_dot_reg<(WA >= 2 ? 2 : WA)>(Ar, Acr, vec);
     }
     const uint4 c = Acols[tid];
     const double *v = Avals + tid;
@@ -670,17 +664,9 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
     const double *v = ATvals + tid;
     double acc;
     if constexpr (TM) {
-      switch (wAT2) {
-        case 1: acc = ell_dot_reg<1>(ATr, ATcr, vec); break;
-        case 2: acc = ell_dot_reg<2>(ATr, ATcr, vec); break;
-        case 3: acc = ell_dot_reg<3>(ATr, ATcr, vec); break;
-        case 4: acc = ell_dot_reg<4>(ATr, ATcr, vec); break;
-        case 5: acc = ell_dot_reg<(WAT2 >= 5 ? 5 : WAT2)>(ATr, ATcr, vec); break;
-        case 6: acc = ell_dot_reg<(WAT2 >= 6 ? 6 : WAT2)>(ATr, ATcr, vec); break;
-        case 7: acc = ell_dot_reg<(WAT2 >= 7 ? 7 : WAT2)>(ATr, ATcr, vec); break;
-        case 8: acc = ell_dot_reg<(WAT2 >= 8 ? 8 : WAT2)>(ATr, ATcr, vec); break;
-        default: acc = 0.0; break;
-      }
+      if (wAT2 > 4) acc = ell_dot_reg<WAT2>(ATr, ATcr, vec);
+      else if (wAT2 > 2) acc = ell_dot_reg<(WAT2 >= 4 ? 4 : WAT2)>(ATr, ATcr, vec);
+      else acc = ell_dot_reg<(WAT2 >= 2 ? 2 : WAT2)>(ATr, ATcr, vec);
       return acc + __shfl_xor_sync(0xffffffffu, acc, 1);
     }
     switch (wAT2) {
@@ -921,6 +907,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         // ---- check_every ADMM iterations
         const int last_it = a.check_every - 1;
         for (int it = 0; it <= last_it; ++it) {
+          uint32_t ca[16], cb[16];          // (dead in the register kernel)
           if (col_warp) {
             const double s = applyAT(vbuf);
             if (has_col && half == 0) rbuf[col] = sigma * x - qv[col] + s;
@@ -930,7 +917,6 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             // S streams out of tensor memory in 16-column chunks (8 doubles), two chunks in flight
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
-            uint32_t ca[16], cb[16];
             auto use = [&](const uint32_t (&c)[16], int q) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
