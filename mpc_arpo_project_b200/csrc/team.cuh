@@ -22,6 +22,9 @@
 #include "sim.cuh"
 
 #define TEAM_THREADS 256
+#ifndef TEAM_TM_CHUNK
+#define TEAM_TM_CHUNK 8        // TMEM columns per tcgen05.ld in the mat-vec (8 or 16)
+#endif
 #ifndef TEAM_CTAS
 #define TEAM_CTAS 2
 #endif
@@ -510,6 +513,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : TMEM_LD_REGS16(r) : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld8x2(uint32_t (&r)[8], uint32_t (&q)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(q[0]), "+r"(q[1]),
+                 "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
@@ -907,7 +919,6 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
         // ---- check_every ADMM iterations
         const int last_it = a.check_every - 1;
         for (int it = 0; it <= last_it; ++it) {
-          uint32_t ca[16], cb[16];          // (dead in the register kernel)
           if (col_warp) {
             const double s = applyAT(vbuf);
             if (has_col && half == 0) rbuf[col] = sigma * x - qv[col] + s;
@@ -917,6 +928,33 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
             // S streams out of tensor memory in 16-column chunks (8 doubles), two chunks in flight
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double2 *r2 = reinterpret_cast<const double2 *>(rbuf + half * HALF);
+#if TEAM_TM_CHUNK == 8
+            uint32_t ca[8], cb[8];                       // 8-column chunks (4 doubles): half the staging registers
+            auto use = [&](const uint32_t (&c)[8], int q) {
+              const double2 r0 = r2[2 * q], r1 = r2[2 * q + 1];
+              a0 = fma(u2d(c[0], c[1]), r0.x, a0);
+              a1 = fma(u2d(c[2], c[3]), r0.y, a1);
+              a2 = fma(u2d(c[4], c[5]), r1.x, a2);
+              a3 = fma(u2d(c[6], c[7]), r1.y, a3);
+            };
+            constexpr int NCH = (2 * HALF) / 8, CW = 8;
+            tmem_ld8(taddr, ca);
+            tmem_ld8(taddr + 8, cb);
+            tmem_wait_ld8x2(ca, cb);
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              if (q & 1) {
+                use(cb, q);
+                if (q + 2 < NCH) tmem_ld8(taddr + 8 * (q + 2), cb);
+              } else {
+                use(ca, q);
+                if (q + 2 < NCH) tmem_ld8(taddr + 8 * (q + 2), ca);
+              }
+              if ((q & 1) && q + 1 < NCH) tmem_wait_ld8x2(ca, cb);
+              if (!(q & 1) && q + 1 < NCH && q + 2 >= NCH) tmem_wait_ld8x2(ca, cb);
+            }
+#else
+            uint32_t ca[16], cb[16];
             auto use = [&](const uint32_t (&c)[16], int q) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -931,7 +969,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
                 }
               }
             };
-            constexpr int NCH = (2 * HALF) / 16;       // full chunks; the remaining (2*HALF - 16*NCH) / 4 doubles pairs come as x4 loads
+            constexpr int NCH = (2 * HALF) / 16, CW = 16;       // full chunks; the remaining (2*HALF - 16*NCH) / 4 doubles pairs come as x4 loads
             tmem_ld16(taddr, ca);
             tmem_ld16(taddr + 16, cb);
             tmem_wait_ld2(ca, cb);
@@ -947,8 +985,9 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
               if ((q & 1) && q + 1 < NCH) tmem_wait_ld2(ca, cb);
               if (!(q & 1) && q + 1 < NCH && q + 2 >= NCH) tmem_wait_ld2(ca, cb);
             }
+#endif
 #pragma unroll
-            for (int c0 = 16 * NCH; c0 < 2 * HALF; c0 += 4) {
+            for (int c0 = CW * NCH; c0 < 2 * HALF; c0 += 4) {
               uint32_t c4[4];
               tmem_ld4(taddr + c0, c4);
               tmem_wait_ld4(c4);
