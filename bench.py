@@ -341,6 +341,27 @@ def main():
     t1 = eng.counters()
     eng.set_timing(False)
 
+    # solver status mix and iterations-per-solve histogram (SURVEY 8(d) caveat): one untimed step that also records the
+    # per-solve status / iteration telemetry, reduced on the host over the live solves
+    mix = None
+    if rank == 0 and wl["kind"] == "D":
+        rec2 = tuple(record) + ("status", "iters")
+        r2 = eng.simulate_discrete(x0_d, noise_d, nsteps, rec2)
+        st = np.asarray(r2.status.cpu() if hasattr(r2.status, "cpu") else r2.status).astype(np.int64)
+        it = np.asarray(r2.iters.cpu() if hasattr(r2.iters, "cpu") else r2.iters).astype(np.int64)
+        iterm = np.asarray(r2.i_term.cpu() if hasattr(r2.i_term, "cpu") else r2.i_term).astype(np.int64)
+        live = np.arange(st.shape[0])[:, None] < iterm[None, :]
+        names = {1: "solved", 2: "solved_inaccurate", -3: "primal_infeasible", 3: "primal_infeasible_inaccurate",
+                 -2: "max_iter_reached"}
+        tot = max(1, int(live.sum()))
+        edges = [25, 50, 75, 100, 200, 500, 1000, 3999, 4000]
+        hist, lo = {}, 0
+        for e in edges:
+            hist[f"<={e}"] = float(((it > lo) & (it <= e) & live).sum() / tot)
+            lo = e
+        mix = {"status_fraction": {nm: float(((st == k) & live).sum() / tot) for k, nm in names.items()},
+               "iters_per_solve_hist": hist}
+
     red = torch.tensor([ms, float(solves), ms_e2e, float(solves_e2e)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = red.clone()
@@ -381,7 +402,8 @@ def main():
                        "mean_admm_iters_per_solve": status["admm_iterations"] / max(1.0, status["qp_solves"]),
                        "live_steps_per_lane": status["qp_solves"] / B,
                        "flip_lanes": status["flip_lanes"], "ukf_clamped_lanes": status["ukf_clamped_lanes"],
-                       "operator_rebuilds_per_step": (c1["operator_rebuilds"] - c0["operator_rebuilds"]) / max(1, args.steps)},
+                       "operator_rebuilds_per_step": (c1["operator_rebuilds"] - c0["operator_rebuilds"]) / max(1, args.steps),
+                       "solver_mix": mix},
             "e2e": {"value": solves_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),

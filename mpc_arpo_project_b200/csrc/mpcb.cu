@@ -104,6 +104,7 @@ struct mpcb_handle {
   double *scache = nullptr, *scache_rho = nullptr;
   int *scache_var = nullptr;
   bool scache_tried = false, team_tm = false;
+  int team_threads = 256;
   int visit_iters = -1;                // list mode: iterations per lane visit; -1 = sized per round, 0 = unlimited (MPCB_VISIT_ITERS)
   size_t team_smem = 0;
   const void *team_fn_ptr = nullptr;
@@ -327,10 +328,16 @@ static void set_warps(mpcb_handle *h, int w) {
 // Team kernel tables: ELL in "team layout" (row r -> thread r % TEAM, slot r / TEAM; entry e of a
 // slot at [(base + e) * TEAM + thread]), the sign-patch list, k-major V per variant.
 typedef void (*team_fn)(const TeamArgs);
-struct TeamShape { int n, m, wa, wat2, wp, ss; team_fn fn; };
-static const TeamShape kTeamShapes[] = {      // Nx = 10, Nc = Nb = 5 (BASELINE configs 2, 3)
-  {81, 136, 8, 6, 4, 0, team_kernel<81, 136, 8, 6, 4, 0, true>},      // operator in tensor memory, A / A' rows in registers
-  {81, 136, 8, 6, 4, 8, team_kernel<81, 136, 8, 6, 4, 8, false>},     // operator in registers + 8 entries per thread in shared memory (MPCB_TEAM=regs)
+struct TeamShape { int n, m, wa, wat2, watx, wp, ss, threads, ctas; team_fn fn; };
+static const TeamShape kTeamShapes[] = {
+  // Nx = 10 (BASELINE configs 2, 3): operator in tensor memory (84 columns per thread, 2 teams per SM), A / A' rows in registers
+  {81, 136, 8, 6, 0, 4, 0, 256, 2, team_kernel<81, 136, 8, 6, 0, 4, 0, true, 256, 2>},
+  // same family, operator in registers + 8 entries per thread in shared memory (MPCB_TEAM=regs)
+  {81, 136, 8, 6, 0, 4, 8, 256, 2, team_kernel<81, 136, 8, 6, 0, 4, 8, false, 256, 2>},
+  // Nx = 20 (config 4): 124 columns per thread, two warps per lane quarter -> 248 of a 256-column allocation, 2 teams per SM
+  {121, 226, 8, 6, 5, 4, 0, 256, 2, team_kernel<121, 226, 8, 6, 5, 4, 0, true, 256, 2>},
+  // Nx = 30 (config 5): 164 columns per thread, three warps per lane quarter -> 492 of 512 columns, one 384-thread team per SM
+  {161, 316, 8, 6, 10, 4, 0, 384, 1, team_kernel<161, 316, 8, 6, 10, 4, 0, true, 384, 1>},
 };
 static const TeamShape *team_shape_for(int n, int m) {
   const char *e = getenv("MPCB_TEAM");
@@ -375,12 +382,14 @@ static int build_team_tables(mpcb_handle *h) {
   }
   for (int q = 0; q < n; ++q) {
     const int w2 = ((int)colsA[colmap[q]].size() + 1) / 2;
-    if (w2 > ts->wat2 || w2 > 8) return MPCB_OK;
+    if (w2 > ts->wat2 + ts->watx || w2 > 16) return MPCB_OK;
     hd.wAT2[(2 * q) / 32] = std::max(hd.wAT2[(2 * q) / 32], w2);
     if ((int)rowsP[colmap[q]].size() > ts->wp) return MPCB_OK;
   }
-  std::vector<double> Av((size_t)ts->wa * mp, 0.0), ATv((size_t)ts->wat2 * nct, 0.0), Pv((size_t)ts->wp * npair, 0.0);
-  std::vector<uint16_t> Ac((size_t)8 * mp, 0), ATc((size_t)8 * nct, 0), Pc((size_t)ts->wp * npair, 0), rmap(mp, 0), cmap(npair, 0);
+  const int wat_all = ts->wat2 + ts->watx;
+  std::vector<double> Av((size_t)ts->wa * mp, 0.0), ATv((size_t)wat_all * nct, 0.0), Pv((size_t)ts->wp * npair, 0.0);
+  std::vector<uint16_t> Ac((size_t)8 * mp, 0), ATc((size_t)8 * nct, 0), ATc2((size_t)8 * nct, 0), Pc((size_t)ts->wp * npair, 0), rmap(mp, 0),
+      cmap(npair, 0);
   for (int t = 0; t < m; ++t) {
     const int r = rowmap[t];
     rmap[t] = (uint16_t)r;
@@ -395,7 +404,8 @@ static int build_team_tables(mpcb_handle *h) {
     for (size_t k = 0; k < colsA[c].size(); ++k) {
       const int tid = 2 * q + (int)(k & 1);
       ATv[(k / 2) * nct + tid] = hp.A_s[(size_t)colsA[c][k] * n + c];
-      ATc[(size_t)tid * 8 + k / 2] = (uint16_t)colsA[c][k];
+      if (k / 2 < 8) ATc[(size_t)tid * 8 + k / 2] = (uint16_t)colsA[c][k];
+      else ATc2[(size_t)tid * 8 + k / 2 - 8] = (uint16_t)colsA[c][k];
     }
     for (size_t e = 0; e < rowsP[c].size(); ++e) {
       Pv[e * npair + q] = hp.P_s[(size_t)c * n + rowsP[c][e]];
@@ -426,7 +436,7 @@ static int build_team_tables(mpcb_handle *h) {
   hd.off_q = take(8 * n); hd.off_D = take(8 * n); hd.off_Dinv = take(8 * n);
   hd.off_E = take(8 * m); hd.off_Einv = take(8 * m); hd.off_lt = take(8 * m); hd.off_ut = take(8 * m);
   hd.off_Av = take(8 * Av.size()); hd.off_ATv = take(8 * ATv.size()); hd.off_Pv = take(8 * Pv.size());
-  hd.off_Ac = take(2 * Ac.size()); hd.off_ATc = take(2 * ATc.size()); hd.off_Pc = take(2 * Pc.size());
+  hd.off_Ac = take(2 * Ac.size()); hd.off_ATc = take(2 * ATc.size()); hd.off_ATc2 = take(2 * ATc2.size()); hd.off_Pc = take(2 * Pc.size());
   hd.off_rowmap = take(2 * rmap.size()); hd.off_colmap = take(2 * cmap.size());
   hd.off_flags = take(m);
   hd.off_patch = take(16 * patch.size());
@@ -445,6 +455,7 @@ static int build_team_tables(mpcb_handle *h) {
   putd(hd.off_Pv, Pv.data(), Pv.size());
   memcpy(b.data() + hd.off_Ac, Ac.data(), Ac.size() * 2);
   memcpy(b.data() + hd.off_ATc, ATc.data(), ATc.size() * 2);
+  memcpy(b.data() + hd.off_ATc2, ATc2.data(), ATc2.size() * 2);
   memcpy(b.data() + hd.off_Pc, Pc.data(), Pc.size() * 2);
   memcpy(b.data() + hd.off_rowmap, rmap.data(), rmap.size() * 2);
   memcpy(b.data() + hd.off_colmap, cmap.data(), cmap.size() * 2);
@@ -471,10 +482,11 @@ static int build_team_tables(mpcb_handle *h) {
   CK(cudaMalloc(&h->d_lam, (size_t)4 * n * 8));
   CK(cudaMemcpy(h->d_lam, hp.lam.data(), (size_t)4 * n * 8, cudaMemcpyHostToDevice));
   h->thdr = hd;
-  const int nw = TEAM_THREADS / 32;
+  const int nw = ts->threads / 32;
   h->team_smem = (size_t)hd.total + 8 * (size_t)(5 * mp + 3 * np2 + 16 * nw + ts->ss * nct) + ((sizeof(UkfScratch) + 15) & ~15) +
                  sizeof(LaneCtx) + 16;
-  h->team_ctas = TEAM_CTAS;
+  h->team_ctas = ts->ctas;
+  h->team_threads = ts->threads;
   h->team_tm = ts->ss == 0;
   h->team_fn_ptr = (const void *)ts->fn;
   CK(cudaFuncSetAttribute(h->team_fn_ptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->team_smem));
@@ -518,7 +530,7 @@ static int launch_team(mpcb_handle *h, const TeamArgs &ta) {
     e1 = h->ev_pool[1];
     CK(cudaEventRecord(e0, h->stream));
   }
-  ((team_fn)h->team_fn_ptr)<<<grid, TEAM_THREADS, h->team_smem, h->stream>>>(ta);
+  ((team_fn)h->team_fn_ptr)<<<grid, h->team_threads, h->team_smem, h->stream>>>(ta);
   CK(cudaGetLastError());
   if (h->timing) {
     CK(cudaEventRecord(e1, h->stream));
@@ -1083,7 +1095,7 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       else ta.visit_iters = (int)std::max<long>(4L * aa.check_every, (live / 10 / aa.check_every) * aa.check_every);
       CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
       const int tgrid = (int)std::min<long>(live, (long)h->num_sms * h->team_ctas);
-      ((team_fn)h->team_fn_ptr)<<<tgrid, TEAM_THREADS, h->team_smem, h->stream>>>(ta);
+      ((team_fn)h->team_fn_ptr)<<<tgrid, h->team_threads, h->team_smem, h->stream>>>(ta);
     } else if (use_tile) {
       TileArgs ta;
       memset(&ta, 0, sizeof ta);

@@ -67,17 +67,18 @@
 struct TeamHdr {
   int off_q, off_D, off_Dinv, off_E, off_Einv, off_lt, off_ut;   // double vectors in natural index order
   int off_Av;       // [WA][MP]    value e of the row thread t owns
-  int off_ATv;      // [WAT2][NCT] value pair-slot e of thread t (entry 2e + (t&1) of column colmap[t>>1])
+  int off_ATv;      // [WAT2+WATX][NCT] value pair-slot e of thread t (entry 2e + (t&1) of column colmap[t>>1])
   int off_Pv;       // [WP][NCT/2] row colmap[p] of P
   int off_Ac;       // [MP] uint4: 8 uint16 column indices of the thread's row
-  int off_ATc;      // [NCT] uint4: 8 uint16 row indices
+  int off_ATc;      // [NCT] uint4: 8 uint16 row indices (pair-slots 0..7)
+  int off_ATc2;     // [NCT] uint4: pair-slots 8..15 (long columns: the disturbance variables touch every dynamics row)
   int off_Pc;       // [WP][NCT/2] uint16
   int off_rowmap;   // [MP] uint16
   int off_colmap;   // [NCT/2] uint16
   int off_flags;                                                 // uint8 per row (natural order)
   int off_patch;                                                 // int4 {offA, offAT, which, 0} per signed entry
   int n_patch;
-  int wA[8], wAT2[8];                                            // per-warp ELL widths
+  int wA[16], wAT2[16];                                          // per-warp ELL widths
   int total;                                                     // bytes, multiple of 16
 };
 
@@ -557,9 +558,11 @@ __device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloi
 // -- is what two teams per SM saturate (tools/ubench_tmem.cu, ubench_lds.cu: every LDS.64 a warp issues costs
 // the pipe a cycle, broadcast or not), so in this mode the registers S vacated hold the thread's rows of A / A'
 // (values and packed column indices), which removes the table loads from every iteration, and SS must be 0.
-template <int N, int M, int WA, int WAT2, int WP, int SS, bool TM>
-__global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __grid_constant__ TeamArgs a) {
-  constexpr int TEAM = TEAM_THREADS;
+// WATX: pair-slots beyond the WAT2 register-resident ones, read from shared memory by the few warps whose columns are
+// that long (Nx = 20 / 30: the two disturbance columns have Nx+1 entries).  TT threads per team, CT teams per SM.
+template <int N, int M, int WA, int WAT2, int WATX, int WP, int SS, bool TM, int TT, int CT>
+__global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ TeamArgs a) {
+  constexpr int TEAM = TT;
   constexpr int HALF = ((N + 3) / 4) * 2;  // entries of a row of S per thread (even); 2*HALF >= N
   constexpr int NP2 = 2 * HALF;            // padded n-vector length in shared memory / Vk row length
   constexpr int MP = (M + 1) & ~1;
@@ -567,8 +570,10 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   constexpr int NCT = ((2 * N + 31) / 32) * 32;   // threads that run the pair phases: whole warps (shuffles stay convergent)
   constexpr int SR = HALF - SS;            // entries of S per thread kept in registers
   static_assert(SS % 2 == 0 && SR % 2 == 0 && SR > 0, "S split must be even");
-  static_assert(!TM || (SS == 0 && HALF > 32 && HALF <= 48 && HALF % 2 == 0 && TEAM <= 256), "tensor-memory mode: 2*HALF columns per thread, two warps per lane quarter");
-  static_assert(2 * N <= TEAM && M <= TEAM && WA <= 8 && WAT2 <= 8, "team too small");
+  constexpr int TNEED = ((TEAM + 127) / 128) * 2 * HALF;     // TMEM columns: (warps per lane quarter) x (columns per thread)
+  constexpr int TALLOC = TNEED <= 128 ? 128 : (TNEED <= 256 ? 256 : 512);
+  static_assert(!TM || (SS == 0 && HALF >= 16 && HALF % 2 == 0 && TNEED <= 512 && CT * TALLOC <= 512), "tensor-memory mode: S does not fit");
+  static_assert(2 * N <= TEAM && M <= TEAM && WA <= 8 && WAT2 <= 8 && WAT2 + WATX <= 16 && (TM || WATX == 0) && TEAM <= 512, "team too small");
   extern __shared__ __align__(128) unsigned char smem[];
   const TeamHdr &h = a.hdr;
   const int tid = threadIdx.x, warp = tid >> 5, lid = tid & 31;
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   __shared__ uint32_t s_tmem;
   if (TM) {
     if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)));
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(TALLOC));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -679,6 +684,21 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
       if (wAT2 > 4) acc = ell_dot_reg<WAT2>(ATr, ATcr, vec);
       else if (wAT2 > 2) acc = ell_dot_reg<(WAT2 >= 4 ? 4 : WAT2)>(ATr, ATcr, vec);
       else acc = ell_dot_reg<(WAT2 >= 2 ? 2 : WAT2)>(ATr, ATcr, vec);
+      if constexpr (WATX > 0) {
+        if (wAT2 > WAT2) {               // warp-uniform: the warp that owns the long columns
+          const uint4 c2 = reinterpret_cast<const uint4 *>(smem + h.off_ATc2)[tid];
+          const unsigned cw[8] = {ATcr.x, ATcr.y, ATcr.z, ATcr.w, c2.x, c2.y, c2.z, c2.w};
+          double acc1 = 0.0;
+#pragma unroll
+          for (int e = WAT2; e < WAT2 + WATX; ++e)
+            if (e < wAT2) {
+              const unsigned idx = (e & 1) ? (cw[e >> 1] >> 16) : (cw[e >> 1] & 0xffffu);
+              if (e & 1) acc1 = fma(ATvals[e * NCT + tid], vec[idx], acc1);
+              else acc = fma(ATvals[e * NCT + tid], vec[idx], acc);
+            }
+          acc += acc1;
+        }
+      }
       return acc + __shfl_xor_sync(0xffffffffu, acc, 1);
     }
     switch (wAT2) {
@@ -831,16 +851,17 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
           if (tid < N) dk[tid] = 1.0 / (1.0 + rho * a.lam[variant * N + tid]);
           __syncthreads();
           if constexpr (TM) {
-            // three passes over V (16 + 16 + (HALF-32) entries of this thread's half row) keep the accumulators small;
-            // the summation order over k is the register version's, so S is bit-identical to it
+            // passes over V, 16 entries of this thread's half row at a time, keep the accumulators small; the summation
+            // order over k is the register version's, so S is bit-identical to it
             if (col_warp) {
               const double *Vk = a.Vk[variant];
 #pragma unroll 1
-              for (int pass = 0; pass < 3; ++pass) {
+              constexpr int NPASS = (HALF + 15) / 16;
+              for (int pass = 0; pass < NPASS; ++pass) {
                 double T[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) T[j] = 0.0;
-                const int cnt2 = (pass < 2) ? 8 : (HALF - 32) / 2;
+                const int cnt2 = (pass < NPASS - 1) ? 8 : (HALF - 16 * (NPASS - 1)) / 2;
                 for (int k = 0; k < N; ++k) {
                   const double *vrow = Vk + (size_t)k * NP2;
                   const double tk = has_col ? __ldg(vrow + col) * dk[k] : 0.0;
@@ -1190,7 +1211,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, TEAM_CTAS) team_kernel(const __g
   TP_FLUSH
   if (TM) {
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(s_tmem));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TALLOC));
   }
   if (tid == 0) {
     if (my_iters) atomicAdd(&a.tot[0], my_iters);
