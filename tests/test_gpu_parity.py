@@ -245,12 +245,37 @@ def test_drop_in_matches_reference_driver_fixture(name):
 
 @pytest.mark.parametrize("dv", [False, True])
 def test_continuous_closed_loop_matches_scalar_oracle(dv):
-    case = dict(Nx=10, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=3, isDeltaV=dv)
+    _continuous_vs_scalar(dict(Nx=10, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=3, isDeltaV=dv))
+
+
+@pytest.mark.parametrize("env", [
+    {"MPCB_VISIT_ITERS": "25"},          # every solve longer than one check period spans several visits of the list-mode kernel
+    {"MPCB_SCACHE_GB": "0"},             # no operator cache: every visit rebuilds S
+    {"MPCB_SOLVER": "block"},            # the warp-per-lane block kernel under the same rounds
+    {"MPCB_SOLVER": "tile"},             # DMMA tile kernel
+    {"MPCB_TEAM": "regs"},               # register-resident operator
+])
+def test_continuous_closed_loop_solver_paths(env, monkeypatch):
+    """The round-based (continuous) simulator gives the same trajectory whichever kernel solves its QPs and however
+    the solves are cut into visits."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _continuous_vs_scalar(dict(Nx=10, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=3, isDeltaV=False))
+
+
+@pytest.mark.parametrize("Nx", [20, 30])
+def test_continuous_closed_loop_longer_horizons(Nx):
+    """n = 121 / 161: tensor-memory team kernels (2 and 1 teams per SM) in list mode, long disturbance columns."""
+    _continuous_vs_scalar(dict(Nx=Nx, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=2, isDeltaV=False))
+
+
+def _continuous_vs_scalar(case):
     B = 2
     x0, rng = lanes(case, B, 9)
     sc, mp, fp, _ = make_params(M, case)
-    nsimD, nsimC, ratio = 6, 3000, 500
-    n_refresh = np.arange(0, 3, 0.5 * 4).size
+    Tf = case['T_final']
+    nsimD, nsimC, ratio = int(Tf / 0.5), int(Tf / 0.001), 500
+    n_refresh = np.arange(0, Tf, 0.5 * 4).size
     V = 0.0012 * rng.standard_normal((B, 2, n_refresh))
     noise = np.ascontiguousarray(V.transpose(2, 1, 0))
     got = M.trajectorySimulateCBatch(sc, mp, fp, None, x0, noise)
