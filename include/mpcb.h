@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 2
+#define MPCB_ABI_VERSION 3
 
 typedef enum mpcb_status {
   MPCB_OK = 0,
@@ -50,6 +50,9 @@ typedef enum mpcb_status {
 #define MPCB_CTRL_FAILSAFE 2
 #define MPCB_CTRL_DEADBEAT 3
 
+#define MPCB_EST_UKF 0
+#define MPCB_EST_KF 1
+
 typedef struct mpcb_handle mpcb_handle;
 
 /* Constant tables of one problem family, built on the host (mpc_arpo_project_b200/problem.py).
@@ -60,6 +63,9 @@ typedef struct mpcb_problem {
   int32_t n, m;                  /* n = 4(Nx+1)+7Nc+2 variables, m = 9(Nx+1)+7Nc+2 rows */
   int32_t in_track, delta_v, is_reject, has_noise;   /* SimConditions flags (src/mpcsim.py:59-73) */
   int32_t noise_length;          /* Noise.noise_length, control steps per disturbance draw */
+  int32_t estimator;             /* MPCB_EST_UKF: range/bearing UKF of src/trajectorySimulate.py:121-130, 329-337 (default);
+                                    MPCB_EST_KF: the linear Kalman filter on position measurements of the reference's
+                                    prototype misc/MPCrendezKALMANdisturb.py:261-266, same call timing */
   /* OSQP settings as the reference leaves them (defaults; :245) */
   double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, adaptive_rho_tolerance;
   int32_t max_iter, check_termination, adaptive_rho, adaptive_rho_interval;

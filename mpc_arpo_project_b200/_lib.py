@@ -23,7 +23,7 @@ class MpcbProblem(C.Structure):
         ("Nx", C.c_int32), ("Nc", C.c_int32), ("Nb", C.c_int32),
         ("n", C.c_int32), ("m", C.c_int32),
         ("in_track", C.c_int32), ("delta_v", C.c_int32), ("is_reject", C.c_int32), ("has_noise", C.c_int32),
-        ("noise_length", C.c_int32),
+        ("noise_length", C.c_int32), ("estimator", C.c_int32),
         ("rho0", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("eps_abs", C.c_double),
         ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("adaptive_rho_tolerance", C.c_double),
         ("max_iter", C.c_int32), ("check_termination", C.c_int32), ("adaptive_rho", C.c_int32),
@@ -86,7 +86,7 @@ SYMBOLS = {
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NSTATS = 10
 _lib = None
 

@@ -48,6 +48,7 @@ struct SimConst {
   double Ad[16], Bd[8], Ao[36], Bou[12], Qw[36], Kpf[8], Kif[2], xr[4];
   double umax0, r_p, r_tol, suc_dist, suc_ang_deg, mean_mtn;
   int in_track, delta_v, is_reject, has_noise, noise_length;
+  int estimator;               // MPCB_EST_UKF | MPCB_EST_KF
 };
 
 struct LaneSim {            // SoA [field][B] per-lane simulation state

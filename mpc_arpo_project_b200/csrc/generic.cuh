@@ -468,8 +468,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           plant_lin(c, L.xtrue, uprev, L.noise, xn);
           double xe[6];
           if (c.has_noise) {
-            const double zm[2] = {sqrt(xn[0] * xn[0] + xn[1] * xn[1]), atan2(xn[1], xn[0])};
-            if (!ukf_step(c, L.ux, L.uP, uprev, zm)) L.ukf_clamp = 1;
+            if (!estimator_step(c, L.ux, L.uP, uprev, xn)) L.ukf_clamp = 1;
             for (int k = 0; k < 6; ++k) xe[k] = L.ux[k];
           } else {
             for (int k = 0; k < 4; ++k) xe[k] = xn[k];

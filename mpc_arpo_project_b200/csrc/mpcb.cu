@@ -778,6 +778,7 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
   const int n = pr->n, m = pr->m;
   if (pr->Nx < 1 || pr->Nc < 1 || pr->Nc > pr->Nx || pr->Nb < 0 || pr->Nb > pr->Nx)
     return fail(MPCB_ERR_INVALID, "bad horizons");
+  if (pr->estimator != MPCB_EST_UKF && pr->estimator != MPCB_EST_KF) return fail(MPCB_ERR_INVALID, "unknown estimator");
   if (n != 4 * (pr->Nx + 1) + 7 * pr->Nc + 2 || m != 9 * (pr->Nx + 1) + 7 * pr->Nc + 2)
     return fail(MPCB_ERR_INVALID, "n/m do not match the horizons");
   const bool debris = pr->has_debris != 0;
@@ -834,6 +835,7 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
   sc.suc_ang_deg = pr->suc_ang_deg; sc.mean_mtn = pr->mean_mtn;
   sc.in_track = pr->in_track; sc.delta_v = pr->delta_v; sc.is_reject = pr->is_reject; sc.has_noise = pr->has_noise;
   sc.noise_length = std::max(1, pr->noise_length);
+  sc.estimator = pr->estimator;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;

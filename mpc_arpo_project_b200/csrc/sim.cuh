@@ -227,6 +227,54 @@ __device__ __forceinline__ int select_control(const PostArgs &a, int ln, int sta
   return code;
 }
 
+// Linear Kalman filter on POSITION measurements, R = 0 -- the estimator of the reference's prototype
+// misc/MPCrendezKALMANdisturb.py:261-266 (restated in oracle/kf_ref.py), called where the simulators call the UKF:
+//   x- = Ao x + Bou u;  P- = Ao P Ao' + Qw;  L = P- Co' (Co P- Co')^-1;  x = x- + L (y - Co x-);  P = (I - L Co) P-
+// with Co = [I2 0].  Always returns true (no Cholesky to clamp).
+__device__ __noinline__ bool kf_step(const SimConst &c, double *x, double *P, const double *u, const double *ymeas) {
+  double xm[6], AP[36], Pm[36];
+  for (int i = 0; i < 6; ++i) {
+    double acc = 0.0;
+    for (int j = 0; j < 6; ++j) acc += c.Ao[i * 6 + j] * x[j];
+    xm[i] = acc + c.Bou[i * 2] * u[0] + c.Bou[i * 2 + 1] * u[1];
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 6; ++k) acc += c.Ao[i * 6 + k] * P[k * 6 + j];
+      AP[i * 6 + j] = acc;
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 6; ++k) acc += AP[i * 6 + k] * c.Ao[j * 6 + k];
+      Pm[i * 6 + j] = acc + c.Qw[i * 6 + j];
+    }
+  const double s00 = Pm[0], s01 = Pm[1], s10 = Pm[6], s11 = Pm[7];
+  const double det = s00 * s11 - s01 * s10;
+  const double i00 = s11 / det, i01 = -s01 / det, i10 = -s10 / det, i11 = s00 / det;
+  double Lg[12];
+  for (int i = 0; i < 6; ++i) {
+    Lg[i * 2] = Pm[i * 6] * i00 + Pm[i * 6 + 1] * i10;
+    Lg[i * 2 + 1] = Pm[i * 6] * i01 + Pm[i * 6 + 1] * i11;
+  }
+  const double r0 = ymeas[0] - xm[0], r1 = ymeas[1] - xm[1];
+  for (int i = 0; i < 6; ++i) x[i] = xm[i] + Lg[i * 2] * r0 + Lg[i * 2 + 1] * r1;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) P[i * 6 + j] = Pm[i * 6 + j] - (Lg[i * 2] * Pm[j] + Lg[i * 2 + 1] * Pm[6 + j]);
+  return true;
+}
+
+// The estimator the problem selects; zsrc = true state the measurement is taken from.
+__device__ __forceinline__ bool estimator_step(const SimConst &c, double *x, double *P, const double *u, const double *xn) {
+  if (c.estimator == MPCB_EST_KF) {
+    const double y[2] = {xn[0], xn[1]};
+    return kf_step(c, x, P, u, y);
+  }
+  const double zm[2] = {sqrt(xn[0] * xn[0] + xn[1] * xn[1]), atan2(xn[1], xn[0])};
+  return ukf_step(c, x, P, u, zm);
+}
+
 // Estimator + QP refresh shared by both simulators (trajectorySimulate.py:329-348).
 // xn: true state the measurement is taken from; uprev: ctrls[:, i]; est_idx: telemetry column.
 __device__ __forceinline__ int estimate_and_refresh(const PostArgs &a, int ln, const double *xn, const double *uprev, int est_idx) {
@@ -236,8 +284,7 @@ __device__ __forceinline__ int estimate_and_refresh(const PostArgs &a, int ln, c
     double ux[6], uP[36];
     for (int i = 0; i < 6; ++i) ux[i] = a.ls.ux[i * B + ln];
     for (int i = 0; i < 36; ++i) uP[i] = a.ls.uP[i * B + ln];
-    const double zm[2] = {sqrt(xn[0] * xn[0] + xn[1] * xn[1]), atan2(xn[1], xn[0])};
-    if (!ukf_step(a.sc, ux, uP, uprev, zm)) a.ls.ukf_clamp[ln] = 1;
+    if (!estimator_step(a.sc, ux, uP, uprev, xn)) a.ls.ukf_clamp[ln] = 1;
     for (int i = 0; i < 6; ++i) a.ls.ux[i * B + ln] = ux[i];
     for (int i = 0; i < 36; ++i) a.ls.uP[i * B + ln] = uP[i];
     for (int i = 0; i < 6; ++i) xe[i] = ux[i];
@@ -522,7 +569,8 @@ __global__ void ukf_step_kernel(SimConst c, int B, double *x, double *P, const d
   double ux[6], uP[36], uu[2] = {u[ln], u[(size_t)B + ln]}, zz[2] = {z[ln], z[(size_t)B + ln]};
   for (int i = 0; i < 6; ++i) ux[i] = x[(size_t)i * B + ln];
   for (int i = 0; i < 36; ++i) uP[i] = P[(size_t)i * B + ln];
-  ukf_step(c, ux, uP, uu, zz);
+  if (c.estimator == MPCB_EST_KF) kf_step(c, ux, uP, uu, zz);      // z = measured position
+  else ukf_step(c, ux, uP, uu, zz);
   for (int i = 0; i < 6; ++i) x[(size_t)i * B + ln] = ux[i];
   for (int i = 0; i < 36; ++i) P[(size_t)i * B + ln] = uP[i];
 }

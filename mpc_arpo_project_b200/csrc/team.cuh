@@ -339,9 +339,17 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
   PS_MARK(0)
   double xe[6];
   if (c.has_noise) {
-    const double z0 = sqrt(xn[0] * xn[0] + xn[1] * xn[1]), z1 = atan2(xn[1], xn[0]);
-    const bool ok = ukf_step_warp(c, L.ux, L.uP, up0, up1, z0, z1, w, lid);
-    if (!ok && lid == 0) L.ukf_clamp = 1;
+    if (c.estimator == MPCB_EST_KF) {          // linear KF: a few hundred flops, one lane does it
+      if (lid == 0) {
+        const double uu[2] = {up0, up1}, yy[2] = {xn[0], xn[1]};
+        kf_step(c, L.ux, L.uP, uu, yy);
+      }
+      __syncwarp();
+    } else {
+      const double z0 = sqrt(xn[0] * xn[0] + xn[1] * xn[1]), z1 = atan2(xn[1], xn[0]);
+      const bool ok = ukf_step_warp(c, L.ux, L.uP, up0, up1, z0, z1, w, lid);
+      if (!ok && lid == 0) L.ukf_clamp = 1;
+    }
     for (int k = 0; k < 6; ++k) xe[k] = L.ux[k];
   } else {
     for (int k = 0; k < 4; ++k) xe[k] = xn[k];

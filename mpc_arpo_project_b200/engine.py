@@ -95,6 +95,7 @@ class Engine:
         cp.Nx, cp.Nc, cp.Nb, cp.n, cp.m = p.Nx, p.Nc, p.Nb, p.n, p.m
         cp.in_track, cp.delta_v, cp.is_reject, cp.has_noise = int(p.in_track), int(p.delta_v), int(p.is_reject), int(p.has_noise)
         cp.noise_length = int(p.noise_length)
+        cp.estimator = int(p.estimator)
         cp.rho0, cp.sigma, cp.alpha = st.rho, st.sigma, st.alpha
         cp.eps_abs, cp.eps_rel, cp.eps_prim_inf = st.eps_abs, st.eps_rel, st.eps_prim_inf
         cp.adaptive_rho_tolerance = st.adaptive_rho_tolerance

@@ -53,6 +53,10 @@ class SolverSettings:
     adaptive_rho_interval: int = 50
     adaptive_rho_tolerance: float = 5.0
     check_termination: int = 25
+    # State estimator (not an OSQP setting; carried here because every entry point already takes ``settings``):
+    # "ukf" = the reference's range/bearing UKF (``trajectorySimulate.py:121-130, 329-337``), "kf" = the linear Kalman
+    # filter on position measurements of the reference's prototype (``misc/MPCrendezKALMANdisturb.py:261-266``).
+    estimator: str = "ukf"
 
 
 def _dense(M):
@@ -179,6 +183,7 @@ class Problem:
     u_off: int = 0               # offset of u_0 in the decision vector
     # debris-avoidance lanes (src/mpcsim.py:99-123): per-lane path, no shared tables
     has_debris: bool = False
+    estimator: int = 0           # 0 = UKF, 1 = linear KF (include/mpcb.h MPCB_EST_*)
     debris_center: np.ndarray = field(default_factory=lambda: np.zeros(2))
     debris_side: float = 0.0
     debris_detect: float = 0.0
@@ -201,6 +206,9 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
     simulator scales the disturbance process noise by ``T*int(T/T_cont)``
     (``trajectorySimulateC.py:310``) instead of ``T`` (``trajectorySimulate.py:272``)."""
     st = settings or SolverSettings()
+    if st.estimator not in ("ukf", "kf"):
+        raise ValueError(f"unknown estimator {st.estimator!r} (\"ukf\" or \"kf\")")
+    est = 1 if st.estimator == "kf" else 0
     sc, mp, fp = sim_conditions, mpc_params, fail_params
     Nx, Nc, Nb = int(mp.Nx), int(mp.Nc), int(mp.Nb)
     nx, nu, ny, nd = 4, 2, 5, 2
@@ -319,7 +327,7 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
                        sgn_rows=np.array(sgn_rows), sgn_c1_col=np.array(c1c), sgn_c2_col=np.array(c2c), row3=np.array(row3),
                        V=None, lam=None, settings=st, u_off=nX, has_debris=True,
                        debris_center=np.asarray(debris.center, float), debris_side=float(debris.side_length),
-                       debris_detect=float(debris.detect_distance), debris_verts=verts, K_dead=K_dead, Ki_dead=Ki_dead)
+                       debris_detect=float(debris.detect_distance), debris_verts=verts, K_dead=K_dead, Ki_dead=Ki_dead, estimator=est)
     P_s, q_s, A_s, D, E, c = ruiz_equilibrate(P, q, A, st.scaling) if st.scaling else (P, q, A, np.ones(n), np.ones(m), 1.0)
     l_s = E * np.maximum(l, -OSQP_INFTY)
     u_s = E * np.minimum(u, OSQP_INFTY)
@@ -337,7 +345,7 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
                    P=P, q=q, A=A, l=l, u=u, D=D, E=E, c=c, P_s=P_s, q_s=q_s, A_s=A_s, l_s=l_s, u_s=u_s, ctype=ctype,
                    sgn_rows=np.array(sgn_rows), sgn_c1_col=np.array(c1c), sgn_c2_col=np.array(c2c),
                    row3=np.array(row3), V=np.zeros((4, n, n)), lam=np.zeros((4, n)), settings=st, u_off=nX,
-                   K_dead=K_dead, Ki_dead=Ki_dead)
+                   K_dead=K_dead, Ki_dead=Ki_dead, estimator=est)
     prob.Qw = _ukf_process_noise(T if ukf_interval_scale is None else ukf_interval_scale, sc)
 
     # ---- spectral operator per sign variant

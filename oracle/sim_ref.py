@@ -32,6 +32,7 @@ import scipy.integrate
 from .control_ref import dlqr_integral, acker, white_noise
 from .osqp_ref import OSQPRef
 from .ukf_ref import UKFRef, MerweScaledSigmaPointsRef
+from .kf_ref import LinearKFRef
 
 
 def _dense(M):
@@ -274,7 +275,14 @@ def build_setup(sc, mp, fp, debris, use_sympy=False):
     return s
 
 
-def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas, chol_fail='raise'):
+def _measure(estimator, x):
+    """UKF: range / bearing of the true state (trajectorySimulate.py:329-332); linear KF: its position (Cm x)."""
+    if estimator == 'kf':
+        return np.array([x[0], x[1]])
+    return np.array([np.linalg.norm(x[:2]), math.atan2(x[1], x[0])])
+
+
+def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas, chol_fail='raise', estimator='ukf'):
     """trajectorySimulate.py:121-130, 250, 272-282 (UKF model, P0, Q, R)."""
     Ao, Bou = s.Ao, s.Bou
 
@@ -289,7 +297,7 @@ def _make_ukf(s, xest0, Bnoise_scale, regen_sigmas, chol_fail='raise'):
     Qw = np.diag([s.sigMat[0, 0] ** 2, s.sigMat[1, 1] ** 2])
     Qw = Bnoise @ Qw @ Bnoise.T
     Qw[:4, :][:, :4] = 0.001 * np.eye(s.nx)
-    kf = UKFRef(6, 2, fx, hx, pts, regen_sigmas=regen_sigmas)
+    kf = UKFRef(6, 2, fx, hx, pts, regen_sigmas=regen_sigmas) if estimator == 'ukf' else LinearKFRef(Ao, Bou)
     kf.x = np.array(xest0, float)
     kf.P = sp.linalg.block_diag(1e-20 * np.eye(s.nx), np.eye(s.ndi))
     kf.R = np.zeros([s.nym, s.nym])
@@ -346,7 +354,7 @@ def _legacy_draw():
 
 # --------------------------------------------------------------------------- discrete
 def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, regen_sigmas=True,
-                        use_sympy=False, max_steps=None, chol_fail='raise'):
+                        use_sympy=False, max_steps=None, chol_fail='raise', estimator='ukf'):
     """trajectorySimulate.py:17-388.  Returns a SimRun-like namespace plus per-step solver
     telemetry (``status_val``, ``iters``, ``rho``, ``u_raw``) used by the parity tests."""
     if draw is None:
@@ -377,7 +385,7 @@ def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, reg
     xestO[:, 0] = xest0
     noiseVec = s.sigMat @ draw()
     noiseStored[:, 0] = noiseVec
-    kf, _ = _make_ukf(s, xest0, s.T, regen_sigmas, chol_fail)
+    kf, _ = _make_ukf(s, xest0, s.T, regen_sigmas, chol_fail, estimator)
 
     status_val = np.zeros(nsim, int)
     iters = np.zeros(nsim, int)
@@ -398,7 +406,7 @@ def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, reg
         xtrueP[:, i + 1] = Ad @ xtrueP[:, i] + Bd @ ctrls[:, i] + noiseVec
 
         if noise is not None:
-            ymeas = np.array([np.linalg.norm(xtrueP[:2, i + 1]), math.atan2(xtrueP[1, i + 1], xtrueP[0, i + 1])])
+            ymeas = _measure(estimator, xtrueP[:, i + 1])
             kf.predict(ctrls[:, i])
             kf.update(ymeas)
             xestO[:, i + 1] = kf.x
@@ -454,7 +462,7 @@ def _substep(x, u, n, t, h, integrator):
 
 
 def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, regen_sigmas=True,
-                          integrator='rk45', use_sympy=False, chol_fail='raise'):
+                          integrator='rk45', use_sympy=False, chol_fail='raise', estimator='ukf'):
     """trajectorySimulateC.py:17-446.  ``V`` (2 x n_refresh) replaces the ``ct.white_noise``
     draw (:301) when given.  The loop's literal start index 500 (:325) is restated as
     ``int(T/T_cont)``, which is what it equals for every shipped parameter set."""
@@ -495,7 +503,7 @@ def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, rege
     for j, col in enumerate(V.T):
         noiseStored[:, j * noiseIntC:noiseIntC * (1 + j)] = np.vstack([col.reshape(ndi, 1), np.zeros([2, 1])])
         sum_vec[:, j * noiseRepeat:noiseRepeat * (1 + j)] = ratio * np.concatenate([col, np.zeros(2)]).reshape(-1, 1)
-    kf, _ = _make_ukf(s, xest0, T * ratio, regen_sigmas, chol_fail)
+    kf, _ = _make_ukf(s, xest0, T * ratio, regen_sigmas, chol_fail, estimator)
 
     status_val, iters, u_raw, solve_at = [], [], [], []
     disc_j = 1
@@ -530,7 +538,7 @@ def trajectory_simulate_c(sc, mp, fp, debris, V=None, solver_settings=None, rege
 
         if sample:
             if noise is not None:
-                ymeas = np.array([np.linalg.norm(xtrueP[:2, i + 1]), math.atan2(xtrueP[1, i + 1], xtrueP[0, i + 1])])
+                ymeas = _measure(estimator, xtrueP[:, i + 1])
                 kf.predict(ctrls[:, i])
                 kf.update(ymeas)
                 xestO[:, disc_j] = kf.x
