@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
 #pragma unroll
                 for (int j = 0; j < 16; ++j) T[j] = 0.0;
                 const int cnt2 = (pass < NPASS - 1) ? 8 : (HALF - 16 * (NPASS - 1)) / 2;
+#pragma unroll 3
                 for (int k = 0; k < N; ++k) {
                   const double *vrow = Vk + (size_t)k * NP2;
                   const double tk = has_col ? __ldg(vrow + col) * dk[k] : 0.0;
