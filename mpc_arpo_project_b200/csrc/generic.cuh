@@ -28,6 +28,9 @@ struct GenArgs {
   double sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol, rho0;
   int check_every, adaptive, adapt_interval, max_iter;
   int mode, nsteps;
+  // continuous simulator (trajectorySimulateC.py): RK4 substeps of T_cont, a solve every `ratio` substeps
+  int ratio, n_sub_total, noise_hold_sub;
+  double T_cont;
   SimConst sc;
   // debris geometry (src/mpcsim.py:99-123) and the deadbeat law (:190-203)
   int has_debris;
@@ -48,6 +51,7 @@ struct GenLane {
   double xtrue[4], ux[6], uP[36], xstore[6], unext[2], noise[2], xfin[4], u0[2];
   double xintf, rho, slope, inter, val, dpin[2], xh[4];
   int step, iterm, succ, nsolve, ukf_clamp, fin, status, iter, lane, c1, c2, side_pos, bound_on;
+  int sub;                   // continuous simulator: next substep index
 };
 
 // simhelpers.py:66-134 for one estimate `xe` (6, in the caller's storage order); fills the per-step QP data.
@@ -171,9 +175,22 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         if (a.out.x_true) for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1) * B + ln] = xe[k];
         if (a.out.x_est) for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1) * B + ln] = xe[k];
         if (a.out.ctrl) for (int k = 0; k < 2; ++k) a.out.ctrl[((size_t)k * T1) * B + ln] = 0.0;
-        L.iterm = a.nsteps;
-        if (a.nsteps <= 0) L.fin = 1;
-        else if (terminated(a.sc, xe)) { L.iterm = 0; L.fin = 1; }
+        if (a.mode == MODE_CONTINUOUS) {     // same prologue as init_kernel (sim.cuh): ratio substeps of x0 with zero control
+          const size_t NS = a.out.NS;
+          const int nfill = min(a.ratio + 1, a.n_sub_total);
+          for (int sdx = 0; sdx < nfill; ++sdx) {
+            if (a.out.x_true_sub) for (int k = 0; k < 4; ++k) a.out.x_true_sub[((size_t)k * NS + sdx) * B + ln] = xe[k];
+            if (a.out.ctrl_sub) for (int k = 0; k < 2; ++k) a.out.ctrl_sub[((size_t)k * NS + sdx) * B + ln] = 0.0;
+          }
+          L.sub = a.ratio;
+          L.iterm = a.n_sub_total;
+          if (a.ratio >= a.n_sub_total - 1) L.fin = 1;
+          else if (terminated(a.sc, xe)) { L.iterm = a.ratio; L.fin = 1; }
+        } else {
+          L.iterm = a.nsteps;
+          if (a.nsteps <= 0) L.fin = 1;
+          else if (terminated(a.sc, xe)) { L.iterm = 0; L.fin = 1; }
+        }
       }
       gen_geometry(a, L, xe);
     }
@@ -463,9 +480,27 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           }
           L.unext[0] = u[0];
           L.unext[1] = u[1];
-          if (i >= 1 && success_cond(c, L.xtrue)) L.succ = 1;
+          if ((i >= 1 || a.mode == MODE_CONTINUOUS) && success_cond(c, L.xtrue)) L.succ = 1;
           for (int k = 0; k < 4; ++k) L.xfin[k] = L.xtrue[k];
-          plant_lin(c, L.xtrue, uprev, L.noise, xn);
+          if (a.mode == MODE_CONTINUOUS) {
+            // trajectorySimulateC.py:325-409, as post_kernel (sim.cuh): the sample substep sees the previous command
+            const double nm = c.mean_mtn, hh = a.T_cont;
+            for (int k = 0; k < 4; ++k) xn[k] = L.xtrue[k];
+            const int nr = min(L.sub / a.noise_hold_sub, a.n_refresh - 1);
+            const double w0 = a.noise_in ? a.noise_in[((size_t)nr * 2 + 0) * B + ln] : 0.0;
+            const double w1 = a.noise_in ? a.noise_in[((size_t)nr * 2 + 1) * B + ln] : 0.0;
+            if (!c.delta_v) {
+              rk4_substep(xn, uprev[0], uprev[1], nm, hh);
+            } else {
+              rk4_substep(xn, 0.0, 0.0, nm, hh);
+              xn[2] += uprev[0];
+              xn[3] += uprev[1];
+            }
+            xn[0] += w0;
+            xn[1] += w1;
+          } else {
+            plant_lin(c, L.xtrue, uprev, L.noise, xn);
+          }
           double xe[6];
           if (c.has_noise) {
             if (!estimator_step(c, L.ux, L.uP, uprev, xn)) L.ukf_clamp = 1;
@@ -483,6 +518,47 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           for (int k = 0; k < 6; ++k) L.xstore[k] = xe[k];
           if (a.out.x_est) for (int k = 0; k < 6; ++k) a.out.x_est[((size_t)k * T1 + i + 1) * B + ln] = xe[k];
           if (a.out.x_true) for (int k = 0; k < 4; ++k) a.out.x_true[((size_t)k * T1 + i + 1) * B + ln] = xn[k];
+          if (a.mode == MODE_CONTINUOUS) {
+            const size_t NS = a.out.NS;
+            const double nm = c.mean_mtn, hh = a.T_cont;
+            int sub = L.sub;
+            auto put_sub = [&](int sdx) {
+              if (a.out.x_true_sub) for (int k = 0; k < 4; ++k) a.out.x_true_sub[((size_t)k * NS + sdx + 1) * B + ln] = xn[k];
+              if (a.out.ctrl_sub) {
+                a.out.ctrl_sub[((size_t)0 * NS + sdx + 1) * B + ln] = u[0];
+                a.out.ctrl_sub[((size_t)1 * NS + sdx + 1) * B + ln] = u[1];
+              }
+              if (a.out.ctrlr_sub) a.out.ctrlr_sub[(size_t)sdx * B + ln] = (uint8_t)code;
+            };
+            put_sub(sub);
+            sub += 1;
+            const int next_sample = (i + 2) * a.ratio;
+            const bool more_samples = (i + 2) < a.nsteps;
+            while (true) {
+              if (sub >= a.n_sub_total - 1) {
+                if (success_cond(c, xn)) L.succ = 1;
+                for (int k = 0; k < 4; ++k) L.xfin[k] = xn[k];
+                L.fin = 1;
+                break;
+              }
+              if (terminated(c, xn)) { L.iterm = sub; L.fin = 1; break; }
+              if (more_samples && sub == next_sample) break;
+              if (success_cond(c, xn)) L.succ = 1;
+              for (int k = 0; k < 4; ++k) L.xfin[k] = xn[k];
+              const int nr = min(sub / a.noise_hold_sub, a.n_refresh - 1);
+              const double w0 = a.noise_in ? a.noise_in[((size_t)nr * 2 + 0) * B + ln] : 0.0;
+              const double w1 = a.noise_in ? a.noise_in[((size_t)nr * 2 + 1) * B + ln] : 0.0;
+              if (!c.delta_v) rk4_substep(xn, u[0], u[1], nm, hh);
+              else rk4_substep(xn, 0.0, 0.0, nm, hh);
+              xn[0] += w0;
+              xn[1] += w1;
+              put_sub(sub);
+              sub += 1;
+            }
+            L.sub = sub;
+            for (int k = 0; k < 4; ++k) L.xtrue[k] = xn[k];
+            L.step = i + 1;
+          } else {
           for (int k = 0; k < 4; ++k) L.xtrue[k] = xn[k];
           if (c.has_noise && ((i + 1) % c.noise_length == 0)) {
             const int r = min((i + 1) / c.noise_length, a.n_refresh - 1);
@@ -492,6 +568,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           L.step = i + 1;
           if (i + 1 >= a.nsteps) L.fin = 1;
           else if (terminated(c, xn)) { L.iterm = i + 1; L.fin = 1; }
+          }
         }
       }
       __syncthreads();
@@ -530,7 +607,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         atomicAdd(&a.stats[4], (double)L.iterm);
         atomicAdd(&a.stats[5], (double)L.nsolve);
         if (L.ukf_clamp) atomicAdd(&a.stats[8], 1.0);
-        if (L.iterm < a.nsteps) atomicAdd(&a.stats[9], 1.0);
+        if (L.iterm < ((a.mode == MODE_CONTINUOUS) ? a.n_sub_total : a.nsteps)) atomicAdd(&a.stats[9], 1.0);
         atomicAdd(&a.tot[1], (unsigned long long)L.nsolve);
       }
     }

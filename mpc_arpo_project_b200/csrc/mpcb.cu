@@ -1393,10 +1393,13 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   CK(cudaEventRecord(h->ev_t0, h->stream));
   CK(cudaMemsetAsync(h->d_stats, 0, MPCB_NSTATS * sizeof(double), h->stream));
   if (h->generic_ok) {
-    if (mode != MODE_DISCRETE) return fail(MPCB_ERR_INVALID, "debris lanes are supported by the discrete simulator only");
     GenArgs g = h->gproto;
-    g.mode = MODE_DISCRETE;
+    g.mode = mode;
     g.nsteps = nsteps;
+    g.ratio = ratio;
+    g.n_sub_total = n_sub_total;
+    g.noise_hold_sub = std::max(1, noise_hold_sub);
+    g.T_cont = T_cont;
     g.out = od;
     g.x0 = d_x0;
     g.noise_in = d_noise;

@@ -269,19 +269,29 @@ def test_continuous_closed_loop_longer_horizons(Nx):
     _continuous_vs_scalar(dict(Nx=Nx, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=2, isDeltaV=False))
 
 
+@pytest.mark.parametrize("case", [
+    dict(Nx=10, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=3, debris=((60., 0.), 5., 20)),
+    # test/traj_eval_radialC.py's obstacle (40, 0) side 5 detect 20, shorter horizon and run
+    dict(Nx=20, sigma=0.0012, noise_length=4, T_cont=0.001, T_final=2, debris=((40., 0.), 5., 20)),
+], ids=["nx10", "radialC_script_debris_nx20"])
+def test_continuous_closed_loop_with_debris(case):
+    """trajectorySimulateC WITH a Debris object (what test/traj_eval_radialC.py calls): per-lane path, RK4 plant."""
+    _continuous_vs_scalar(case)
+
+
 def _continuous_vs_scalar(case):
     B = 2
     x0, rng = lanes(case, B, 9)
-    sc, mp, fp, _ = make_params(M, case)
+    sc, mp, fp, debris = make_params(M, case)
     Tf = case['T_final']
     nsimD, nsimC, ratio = int(Tf / 0.5), int(Tf / 0.001), 500
     n_refresh = np.arange(0, Tf, 0.5 * 4).size
     V = 0.0012 * rng.standard_normal((B, 2, n_refresh))
     noise = np.ascontiguousarray(V.transpose(2, 1, 0))
-    got = M.trajectorySimulateCBatch(sc, mp, fp, None, x0, noise)
+    got = M.trajectorySimulateCBatch(sc, mp, fp, debris, x0, noise)
     for b in range(B):
         sc.x0 = x0[b].copy()
-        r = trajectory_simulate_c(sc, mp, fp, None, V=V[b], integrator='rk4', chol_fail='clamp')
+        r = trajectory_simulate_c(sc, mp, fp, debris, V=V[b], integrator='rk4', chol_fail='clamp')
         assert got.i_term[b] == r.i_term
         ns = len(r.iters)
         assert list(got.iters[:ns, b]) == list(r.iters)
