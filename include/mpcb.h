@@ -183,6 +183,14 @@ int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub_total, int
 #define MPCB_NSTATS 10
 int mpcb_stats(mpcb_handle *h, int64_t B, double *stats, int io_on_device);
 
+/* Disturbance draws on the device: noise[n_refresh][2][B] = (sigma_x, sigma_y) .* N(0,1) from Philox4x32-10, one block per
+ * (lane + lane_offset, refresh), key = seed -- the reference's model `sigMat @ random.normal(0,1,4)` per noise_length steps
+ * (src/trajectorySimulate.py:268, 351-356: four draws, the two position entries used), not numpy's stream.  raw (optional,
+ * may be NULL): the generator's words [n_refresh][4][B] for known-answer tests.  lane_offset = rank * B keeps the ranks of a
+ * multi-GPU run on disjoint streams. */
+int mpcb_noise_fill(mpcb_handle *h, int64_t B, int32_t n_refresh, double sigma_x, double sigma_y, uint64_t seed,
+                    uint64_t lane_offset, double *noise, uint32_t *raw, int io_on_device);
+
 /* Bench utility (no reference counterpart): float64 peak of the device in TFLOP/s, measured with a
  * register-resident DFMA loop (use_dmma = 0) or mma.sync.m8n8k4.f64 loop (use_dmma = 1); the roofline
  * denominators for this float64 path (MEASURED_PEAKS.json has none). */

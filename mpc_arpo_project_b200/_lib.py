@@ -83,6 +83,8 @@ SYMBOLS = {
     "mpcb_simulate_continuous": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_int32, C.POINTER(MpcbSimOut), C.c_int]),
     "mpcb_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "mpcb_noise_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_void_p,
+                                  C.c_void_p, C.c_int]),
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 

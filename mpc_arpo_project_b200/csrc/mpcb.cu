@@ -1475,6 +1475,25 @@ extern "C" int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub
                   io_on_device);
 }
 
+extern "C" int mpcb_noise_fill(mpcb_handle *h, int64_t B, int32_t n_refresh, double sigma_x, double sigma_y, uint64_t seed,
+                               uint64_t lane_offset, double *noise, uint32_t *raw, int io_on_device) {
+  if (!h || !noise || B < 1 || n_refresh < 1 || n_refresh > 65535) return fail(MPCB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  Stage st(&h->stage_pool);
+  double *d_noise;
+  uint32_t *d_raw = nullptr;
+  RC(st.out(noise, (size_t)n_refresh * 2 * B, io_on_device, &d_noise));
+  if (raw) RC(st.out(raw, (size_t)n_refresh * 4 * B, io_on_device, &d_raw));
+  const dim3 grid((unsigned)((B + 127) / 128), (unsigned)n_refresh);
+  noise_fill_kernel<<<grid, 128, 0, h->stream>>>((int)B, n_refresh, sigma_x, sigma_y, seed, lane_offset, d_noise, d_raw);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
+  RC(st.back(noise, d_noise, (size_t)n_refresh * 2 * B, io_on_device, h->stream));
+  if (raw) RC(st.back(raw, d_raw, (size_t)n_refresh * 4 * B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MPCB_OK;
+}
+
 extern "C" int mpcb_stats(mpcb_handle *h, int64_t B, double *stats_out, int io_on_device) {
   if (!h || !stats_out) return fail(MPCB_ERR_INVALID, "null argument");
   if (!h->sim_done || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_stats needs a finished simulation of the same batch");

@@ -563,6 +563,40 @@ __global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__re
 }
 
 // ---- unit seams -------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Disturbance draws on the device: Philox4x32-10 (Salmon et al. SC'11 / Random123; oracle/philox_ref.py pins it to the
+// published known-answer vectors).  One 4-word block per (lane, refresh): counter = (lane lo, lane hi, refresh, 0),
+// key = seed; words 0,1 -> one Box-Muller pair = the two position disturbances, words 2,3 unused -- the reference draws
+// random.normal(0,1,4) and uses two (src/trajectorySimulate.py:268, 351-356).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__global__ void noise_fill_kernel(int B, int n_refresh, double sx, double sy, unsigned long long seed, unsigned long long lane_offset,
+                                  double *__restrict__ noise /*[R][2][B]*/, uint32_t *__restrict__ raw /*[R][4][B] or null*/) {
+  const int ln = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (ln >= B || r >= n_refresh) return;
+  const unsigned long long lane = (unsigned long long)ln + lane_offset;
+  uint32_t c[4] = {(uint32_t)lane, (uint32_t)(lane >> 32), (uint32_t)r, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  if (raw)
+    for (int k = 0; k < 4; ++k) raw[((size_t)r * 4 + k) * B + ln] = c[k];
+  const double u0 = ((double)c[0] + 0.5) * (1.0 / 4294967296.0), u1 = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+  const double rad = sqrt(-2.0 * log(u0));
+  double sn, cs;
+  sincospi(2.0 * u1, &sn, &cs);
+  noise[((size_t)r * 2 + 0) * B + ln] = sx * rad * cs;
+  noise[((size_t)r * 2 + 1) * B + ln] = sy * rad * sn;
+}
+
 __global__ void ukf_step_kernel(SimConst c, int B, double *x, double *P, const double *u, const double *z) {
   const int ln = blockIdx.x * blockDim.x + threadIdx.x;
   if (ln >= B) return;

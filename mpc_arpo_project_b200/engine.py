@@ -198,6 +198,25 @@ class Engine:
                                           ar.ptr(u, shape=(2, B)), ar.ptr(z, shape=(2, B)), int(ar.on_device)))
         return x, P
 
+    def noise_fill(self, B: int, n_refresh: int, seed: int, lane_offset: int = 0, on_device: bool = False, raw: bool = False):
+        """Disturbance tensor ``[n_refresh, 2, B]`` drawn on the GPU (Philox4x32-10, ``mpcb_noise_fill``): ``sigma`` of the
+        problem times N(0, 1), one generator block per (lane + lane_offset, refresh).  ``on_device``: return a torch CUDA
+        tensor (stays in HBM for the simulators) instead of a numpy array.  ``raw``: also return the generator words."""
+        p = self.problem
+        if on_device:
+            import torch
+            dev = torch.device("cuda", self.device)
+            noise = torch.empty((n_refresh, 2, B), dtype=torch.float64, device=dev)
+            words = torch.empty((n_refresh, 4, B), dtype=torch.int32, device=dev) if raw else None
+            np_, wp_ = noise.data_ptr(), (words.data_ptr() if raw else None)
+        else:
+            noise = np.empty((n_refresh, 2, B))
+            words = np.empty((n_refresh, 4, B), dtype=np.uint32) if raw else None
+            np_, wp_ = noise.ctypes.data, (words.ctypes.data if raw else None)
+        _lib.check(self.lib.mpcb_noise_fill(self._h, B, int(n_refresh), float(p.sig[0]), float(p.sig[1]), int(seed) & (2 ** 64 - 1),
+                                            int(lane_offset), np_, wp_, int(on_device)))
+        return (noise, words) if raw else noise
+
     def plant_lin_step(self, x, u, w=None):
         B = x.shape[1]
         ar = _Arrays(x, self.device)

@@ -46,18 +46,24 @@ def _rank() -> int:
         return 0
 
 
-def _run(sc, mp, fp, debris, x0, noise, device):
+def _run(sc, mp, fp, debris, x0, noise, device, philox=None):
+    """``philox = (n_refresh, seed, lane_offset)``: draw the disturbances on the GPU (``Engine.noise_fill``) instead of
+    taking ``noise`` from the host."""
     eng = Engine(build_problem(sc, mp, fp, debris), device)
     try:
+        if philox is not None and sc.noise is not None:
+            noise = eng.noise_fill(x0.shape[1], philox[0], philox[1], philox[2])
         return eng.simulate_discrete(x0, noise, n_control_steps(sc), record=())
     finally:
         eng.close()
 
 
 def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, noise_std: Sequence[float],
-                               noise_lengths: Sequence[float], mc_num: int = 100, seed: int = 0, device: int = 0) -> dict:
+                               noise_lengths: Sequence[float], mc_num: int = 100, seed: int = 0, device: int = 0,
+                               noise_rng: str = "numpy") -> dict:
     """``dist_ratios[i] = mean_j ||x_final(rej) - xr|| / mean_j ||x_final(no rej) - xr||`` for hold length i
-    (``disturbRejComp.py:85-98``).  Returns the ratios and both means; ``mc_num`` lanes per rank and setting."""
+    (``disturbRejComp.py:85-98``).  Returns the ratios and both means; ``mc_num`` lanes per rank and setting.
+    ``noise_rng="philox"``: draws come from the device generator (stream = seed + hold-length index, lanes offset by rank)."""
     x0 = np.tile(np.asarray(sim_conditions.x0, float)[:, None], (1, mc_num))
     nsteps = n_control_steps(sim_conditions)
     rng = np.random.default_rng(seed + 7919 * _rank())
@@ -65,13 +71,14 @@ def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, 
     means = np.zeros((len(noise_lengths), 2))
     for i, nl in enumerate(noise_lengths):
         R = noise_refreshes(nsteps, int(nl))
-        noise = rng.standard_normal((R, 2, mc_num)) * sig[None, :, None]
+        noise = rng.standard_normal((R, 2, mc_num)) * sig[None, :, None] if noise_rng == "numpy" else None
         sums = np.zeros(4)
         for k, rej in enumerate((False, True)):
             sc = copy.copy(sim_conditions)
             sc.isReject = rej
             sc.noise = Noise(tuple(noise_std), int(nl))
-            run = _run(sc, mpc_params, fail_params, debris, x0, noise, device)
+            run = _run(sc, mpc_params, fail_params, debris, x0, noise, device,
+                       None if noise_rng == "numpy" else (R, seed + i, _rank() * mc_num))
             sums[2 * k] = run.stats["sum_final_dist"]
             sums[2 * k + 1] = run.stats["n_lanes"]
         sums = _allreduce_sum(sums, device)
@@ -81,15 +88,18 @@ def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, 
 
 
 def success_rate(sim_conditions, mpc_params, fail_params, debris, mc_num: int = 300, seed: int = 0, device: int = 0,
-                 x0_batch: Optional[np.ndarray] = None) -> dict:
+                 x0_batch: Optional[np.ndarray] = None, noise_rng: str = "numpy") -> dict:
     """Fraction of successful approaches over ``mc_num`` noise realisations (``success_rates_test.py:66-75``)."""
     x0 = np.tile(np.asarray(sim_conditions.x0, float)[:, None], (1, mc_num)) if x0_batch is None else np.ascontiguousarray(x0_batch.T)
     nsteps = n_control_steps(sim_conditions)
-    noise = None
+    noise, philox = None, None
     if sim_conditions.noise is not None:
-        rng = np.random.default_rng(seed + 7919 * _rank())
         R = noise_refreshes(nsteps, int(sim_conditions.noise.noise_length))
-        noise = rng.standard_normal((R, 2, x0.shape[1])) * np.asarray(sim_conditions.noise.noise_std, float)[None, :, None]
-    run = _run(sim_conditions, mpc_params, fail_params, debris, x0, noise, device)
+        if noise_rng == "numpy":
+            rng = np.random.default_rng(seed + 7919 * _rank())
+            noise = rng.standard_normal((R, 2, x0.shape[1])) * np.asarray(sim_conditions.noise.noise_std, float)[None, :, None]
+        else:
+            philox = (R, seed, _rank() * x0.shape[1])
+    run = _run(sim_conditions, mpc_params, fail_params, debris, x0, noise, device, philox)
     s = _allreduce_sum(np.array([run.stats["n_success"], run.stats["n_lanes"]]), device)
     return {"success_count": int(s[0]), "runs": int(s[1]), "success_rate": s[0] / s[1]}

@@ -31,13 +31,16 @@ def noise_refreshes(nsteps: int, noise_length: int) -> int:
 def trajectorySimulateBatch(sim_conditions, mpc_params, fail_params, debris, x0_batch, noise_batch=None,
                             seed: Optional[int] = None, nsteps: Optional[int] = None,
                             record: Sequence[str] = _RECORD_ALL, settings: Optional[SolverSettings] = None,
-                            device: int = 0, engine: Optional[Engine] = None) -> BatchSimRun:
+                            device: int = 0, engine: Optional[Engine] = None, noise_rng: str = "numpy",
+                            lane_offset: int = 0) -> BatchSimRun:
     """B trajectories of ``trajectorySimulate`` on one GPU.
 
     ``x0_batch[B, 4]`` initial states (``sim_conditions.x0`` is ignored); ``noise_batch[R, 2, B]``
     sigma-scaled position disturbances, row ``r`` held from control step ``r*noise_length`` (the
     reference draws ``sigMat @ N(0,1)^4`` there, ``:268,352``); if omitted and the conditions carry a
-    ``Noise``, they are drawn from ``numpy.random.default_rng(seed)``.  Arrays may be numpy or torch
+    ``Noise``, they are drawn from ``numpy.random.default_rng(seed)`` or, with ``noise_rng="philox"``, on the GPU
+    (``Engine.noise_fill``: Philox4x32-10 keyed by ``seed``, lane ``lane_offset + b``; nothing crosses PCIe when ``x0_batch``
+    is a device tensor).  Arrays may be numpy or torch
     CUDA tensors in the engine's SoA layout: pass ``x0_batch`` as ``[4, B]`` torch tensors to skip
     every host copy.
     """
@@ -55,11 +58,16 @@ def trajectorySimulateBatch(sim_conditions, mpc_params, fail_params, debris, x0_
             x0 = np.ascontiguousarray(x0_batch.T)
         if p.has_noise and noise_batch is None:
             R = noise_refreshes(nsteps, p.noise_length)
-            rng = np.random.default_rng(seed)
-            noise_batch = rng.standard_normal((R, 2, B)) * p.sig[None, :, None]
-            if on_dev:
-                import torch
-                noise_batch = torch.from_numpy(noise_batch).to(x0.device)
+            if noise_rng == "philox":
+                noise_batch = eng.noise_fill(B, R, 0 if seed is None else seed, lane_offset, on_device=on_dev)
+            elif noise_rng == "numpy":
+                rng = np.random.default_rng(seed)
+                noise_batch = rng.standard_normal((R, 2, B)) * p.sig[None, :, None]
+                if on_dev:
+                    import torch
+                    noise_batch = torch.from_numpy(noise_batch).to(x0.device)
+            else:
+                raise ValueError(f"unknown noise_rng {noise_rng!r}")
         if not p.has_noise:
             noise_batch = None
         return eng.simulate_discrete(x0, noise_batch, nsteps, record)
