@@ -330,8 +330,12 @@ def main():
     # the sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML init, ~0.3 s) stalls the GPU it queries and
     # would otherwise inflate one of the first timed steps by 20-30 ms; its steady 100 ms polling does not show
     sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    keep = None
     for _ in range(args.warmup):
-        step(True)
+        keep = step(True)       # the previous result stays alive while the next step allocates, exactly as in the timed loop:
+                                # otherwise the second timed step is the first to need a second 120 MB telemetry set and
+                                # pays a cudaMalloc (10-350 ms) inside its timed region
+    del keep
     c0 = eng.counters()
     sync_all()
     ms, solves, res = timed(args.steps, True)
