@@ -1,32 +1,31 @@
-// Team kernel: one CTA ("team", 256 threads) owns one trajectory at a time and runs its WHOLE
-// closed loop (every control step: OSQP-equivalent ADMM solve -> controller select / clip -> plant
-// step -> UKF -> QP parameter refresh) without returning to the host.  Teams pull trajectories from
-// an atomic queue until the batch is exhausted (persistent grid, 2 CTAs per SM).
+// Team kernel: one CTA ("team", 256 or 384 threads) owns one trajectory at a time.  Discrete simulator: the team runs
+// the trajectory's WHOLE closed loop (every control step: OSQP-equivalent ADMM solve -> controller select / clip ->
+// plant step -> UKF -> QP parameter refresh) without returning to the host.  Round-based simulators (continuous
+// plant): "list mode", the team solves the QP of every lane in this round's lists.  Teams pull lanes from an atomic
+// queue until the batch / the lists are exhausted (persistent grid, 2 teams per SM at Nx = 10 / 20, 1 at Nx = 30).
 //
 // Linear solve.  OSQP refactors its KKT matrix whenever rho changes (reference
 // src/trajectorySimulate.py:296 -> osqp_solve / adapt_rho).  Here the reduced operator
 //     S(rho) = (P + sigma I + A' diag(rho_vec) A)^-1 = V diag(1/(1+rho*lam)) V'
-// (spectral tables V, lam per sign variant, built once on the host, problem.py) is materialised
-// per trajectory IN REGISTERS: threads 2i and 2i+1 hold the two halves of row i of S (HALF doubles
-// each), so one ADMM iteration is ONE dense mat-vec with zero shared-memory traffic for the
-// matrix; r is broadcast from shared memory with 128-bit loads and the two half sums meet in a
-// shuffle.  S is rebuilt (N^3 FMAs across the team) only when the trajectory's rho adapts or its
-// velocity-sign variant flips.
+// (spectral tables V, lam per sign variant, built once on the host, problem.py) is materialised per trajectory ON
+// CHIP: threads 2i and 2i+1 own the two halves of row i of S (HALF doubles each), so one ADMM iteration is ONE dense
+// mat-vec.  TM = true (default): S lives in TENSOR MEMORY, 2*HALF 32-bit columns of the thread's own TMEM lane
+// (tcgen05.st at a rebuild, tcgen05.ld in 8-column chunks inside the mat-vec) and the registers hold the thread's
+// rows of A / A'; TM = false: S in registers (+ SS entries per thread in shared memory), A / A' in shared memory.
+// r is broadcast from shared memory with 128-bit loads and the two half sums meet in a shuffle.  S is rebuilt
+// (N^3 FMAs across the team) only when the trajectory's rho adapts or its velocity-sign variant flips; in list mode
+// it is parked in / reloaded from a per-lane cache in HBM between visits.
 //
 // Per iteration (3 team barriers):
 //     r  = sigma*x - q + A'v        (thread pair per entry of r, ELL)      -> smem, barrier
-//     xt = S r ; x = a*xt+(1-a)*x   (thread pair per row, S in registers)  -> smem, barrier
+//     xt = S r ; x = a*xt+(1-a)*x   (thread pair per row of S)             -> smem, barrier
 //     zt = A xt ; z,y update ; v = rho_vec.*z - y  (thread per row, ELL)   -> smem, barrier
 #pragma once
 #include "common.cuh"
 #include "sim.cuh"
 
-#define TEAM_THREADS 256
 #ifndef TEAM_TM_CHUNK
 #define TEAM_TM_CHUNK 8        // TMEM columns per tcgen05.ld in the mat-vec (8 or 16)
-#endif
-#ifndef TEAM_CTAS
-#define TEAM_CTAS 2
 #endif
 
 // Optional cycle breakdown (compile with -DTEAM_PROFILE): thread 0 of every team accumulates clock64()
