@@ -23,7 +23,8 @@ struct GenArgs {
   const int *rowptr, *colidx, *colptr, *rowidx, *cscpos;
   const double *baseA;        // [nnzA]
   const unsigned char *kindA; // 0 constant, 1 carries sign(vx_hat), 2 sign(vy_hat), 3 carries -slope
-  const int *prow, *pcol;     // P in COO (both triangles)
+  const int *prow, *pcol;     // P in COO (both triangles), row-major
+  const int *prowptr;         // [n+1] first COO entry of every row
   const double *pval, *q_u, *l_u, *u_u;
   double sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol, rho0;
   int check_every, adaptive, adapt_interval, max_iter;
@@ -291,17 +292,30 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
       while (st == -10) {
         if (need_op) {
           for (int i = tid; i < m; i += T) rv[i] = ctype[i] == -1 ? MPCB_RHO_MIN : (ctype[i] == 1 ? MPCB_RHO_EQ * rho : rho);
-          for (int o = tid; o < n * n; o += T) S[o] = 0.0;
+          // M = P + sigma I + A' diag(rho_vec) A, entry by entry in a FIXED summation order (rows ascending: the two CSC
+          // columns are merged), so a lane's iterates do not depend on the order atomics happen to land in
           __syncthreads();
-          for (int e = tid; e < nnzP; e += T) atomicAdd(&S[(size_t)a.prow[e] * n + a.pcol[e]], Ps[e]);
-          for (int j = tid; j < n; j += T) atomicAdd(&S[(size_t)j * n + j], a.sigma);
-          for (int i = tid; i < m; i += T) {
-            const int e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
-            for (int ea = e0; ea < e1; ++ea) {
-              const double w = rv[i] * As[ea];
-              for (int eb = e0; eb < e1; ++eb) atomicAdd(&S[(size_t)a.colidx[ea] * n + a.colidx[eb]], w * As[eb]);
+          for (int o = tid; o < n * n; o += T) {
+            const int ci = o / n, cj = o - ci * n;
+            int ea = a.colptr[ci], eb = a.colptr[cj];
+            const int ea1 = a.colptr[ci + 1], eb1 = a.colptr[cj + 1];
+            double acc = (ci == cj) ? a.sigma : 0.0;
+            while (ea < ea1 && eb < eb1) {
+              const int ra = a.rowidx[ea], rb_ = a.rowidx[eb];
+              if (ra == rb_) {
+                acc = fma(rv[ra] * As[a.cscpos[ea]], As[a.cscpos[eb]], acc);
+                ++ea;
+                ++eb;
+              } else if (ra < rb_) {
+                ++ea;
+              } else {
+                ++eb;
+              }
             }
+            S[o] = acc;
           }
+          __syncthreads();
+          for (int e = tid; e < nnzP; e += T) S[(size_t)a.prow[e] * n + a.pcol[e]] += Ps[e];       // COO entries are unique
           __threadfence_block();
           __syncthreads();
           // in-place Gauss-Jordan inversion (M is symmetric positive definite: no pivoting)
@@ -359,9 +373,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           mu[0] = fmax(mu[0], fabs(ei * pv)); mu[1] = fmax(mu[1], fabs(ei * z[i])); mu[2] = fmax(mu[2], fabs(ei * Ax));
           mu[3] = fmax(mu[3], fabs(pv)); mu[4] = fmax(mu[4], fabs(z[i])); mu[5] = fmax(mu[5], fabs(Ax));
         }
-        for (int j = tid; j < n; j += T) xt[j] = 0.0;
-        __syncthreads();
-        for (int e = tid; e < nnzP; e += T) atomicAdd(&xt[a.prow[e]], Ps[e] * x[a.pcol[e]]);     // xt <- P x
+        for (int j = tid; j < n; j += T) {                                                       // xt <- P x, fixed order
+          double acc = 0.0;
+          for (int e = a.prowptr[j]; e < a.prowptr[j + 1]; ++e) acc = fma(Ps[e], x[a.pcol[e]], acc);
+          xt[j] = acc;
+        }
         __syncthreads();
         for (int j = tid; j < n; j += T) {
           const double Px = xt[j], Aty = ATcol(j, v), dv = qs[j] + Px + Aty, di = Dinv[j];

@@ -720,6 +720,9 @@ static int build_generic_tables(mpcb_handle *h) {
         pcol.push_back(c);
         pval.push_back(hp.P_u[(size_t)r * n + c]);
       }
+  std::vector<int> prowptr(n + 1, 0);
+  for (int r : prow) prowptr[r + 1]++;
+  for (int r = 0; r < n; ++r) prowptr[r + 1] += prowptr[r];
   GenArgs &g = h->gproto;
   memset(&g, 0, sizeof g);
   g.n = n; g.m = m; g.nX = nX; g.Nx = p.Nx; g.Nb = p.Nb; g.Nc = p.Nc; g.uoff = nX;
@@ -727,6 +730,7 @@ static int build_generic_tables(mpcb_handle *h) {
   RC(gen_upload(h, rowptr, &g.rowptr)); RC(gen_upload(h, colidx, &g.colidx)); RC(gen_upload(h, colptr, &g.colptr));
   RC(gen_upload(h, rowidx, &g.rowidx)); RC(gen_upload(h, cscpos, &g.cscpos)); RC(gen_upload(h, base, &g.baseA));
   RC(gen_upload(h, kind, &g.kindA)); RC(gen_upload(h, prow, &g.prow)); RC(gen_upload(h, pcol, &g.pcol));
+  RC(gen_upload(h, prowptr, &g.prowptr));
   RC(gen_upload(h, pval, &g.pval)); RC(gen_upload(h, hp.q_u, &g.q_u)); RC(gen_upload(h, hp.l_u, &g.l_u));
   RC(gen_upload(h, hp.u_u, &g.u_u));
   g.sigma = p.sigma; g.alpha = p.alpha; g.eps_abs = p.eps_abs; g.eps_rel = p.eps_rel; g.eps_pinf = p.eps_prim_inf;

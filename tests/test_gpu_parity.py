@@ -477,6 +477,26 @@ def test_debris_lanes_match_scalar_oracle(case, tol):
         np.testing.assert_allclose(got.x_est[:, :Tc + 1, b], r.x_est[:, :Tc + 1], rtol=X_RTOL, atol=tol * X_ATOL)
 
 
+def test_results_are_reproducible_run_to_run():
+    """Same inputs, same outputs, bit for bit: lanes are scheduled dynamically (atomic queue, two teams per SM) but no
+    floating-point result may depend on it.  Debris lanes included (their M = P + sigma I + A'RA was once accumulated
+    with atomics)."""
+    for case, B in ((dict(Nx=10, sigma=0.75, noise_length=50, T_final=40), 600),
+                    (dict(Nx=10, sigma=0.5, noise_length=6, T_final=15, debris=((60., 0.), 5., 20)), 40)):
+        x0, rng = lanes(case, B, 23)
+        sc, mp, fp, debris = make_params(M, case)
+        nsim = int(case['T_final'] / 0.5)
+        noise = case['sigma'] * rng.standard_normal((nsim // case['noise_length'] + 1, 2, B))
+        runs = [M.trajectorySimulateBatch(sc, mp, fp, debris, x0, noise) for _ in range(3)]
+        for r in runs[1:]:
+            np.testing.assert_array_equal(r.i_term, runs[0].i_term)
+            np.testing.assert_array_equal(r.iters, runs[0].iters)
+            np.testing.assert_array_equal(r.status, runs[0].status)
+            assert np.array_equal(r.x_true, runs[0].x_true, equal_nan=True)
+            assert np.array_equal(r.x_est, runs[0].x_est, equal_nan=True)
+            assert np.array_equal(r.ctrl_hist, runs[0].ctrl_hist, equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------ Monte-Carlo drivers
 def test_monte_carlo_reductions_match_per_lane_results():
     """disturbRejComp / success_rates_test as batched calls: the device-side statistics equal what the
