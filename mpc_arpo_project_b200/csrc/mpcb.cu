@@ -102,6 +102,7 @@ struct mpcb_handle {
   int *d_queue = nullptr;
   // per-lane operator cache of the tensor-memory team kernel (list mode), allocated on first use
   double *scache = nullptr, *scache_rho = nullptr;
+  double *ocache = nullptr;            // per-team operator cache of the whole-loop modes (TeamArgs::ocache)
   int *scache_var = nullptr;
   bool scache_tried = false, team_tm = false;
   int team_threads = 256;
@@ -488,6 +489,13 @@ static int build_team_tables(mpcb_handle *h) {
   h->team_ctas = ts->ctas;
   h->team_threads = ts->threads;
   h->team_tm = ts->ss == 0;
+  if (h->team_tm && n > 100 && !getenv("MPCB_NO_OCACHE")) {   // (team.cuh: OC)       // [grid][TEAM_OPC] operators; stays L2-resident for the small families
+    const size_t per_op = (size_t)((n + 3) / 4) * nct * 16;
+    if (cudaMalloc(&h->ocache, per_op * TEAM_OPC * (size_t)h->num_sms * ts->ctas) != cudaSuccess) {
+      cudaGetLastError();
+      h->ocache = nullptr;
+    }
+  }
   h->team_fn_ptr = (const void *)ts->fn;
   CK(cudaFuncSetAttribute(h->team_fn_ptr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->team_smem));
   h->team_ok = true;
@@ -512,6 +520,7 @@ static void fill_team_args(mpcb_handle *h, TeamArgs &ta, int mode) {
   ta.xs = h->xs; ta.zs = h->zs; ta.ys = h->ys; ta.rho = h->rho; ta.u0 = h->u0;
   ta.iter = h->iter; ta.status = h->status; ta.flip = h->flip;
   ta.queue = h->d_queue;
+  ta.ocache = h->ocache;
   ta.tot = h->d_tot;
   ta.stats = h->d_stats;
 }
@@ -901,6 +910,7 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
   cudaFree(h->d_lam);
   cudaFree(h->d_queue);
   for (int v = 0; v < 4; ++v) cudaFree(h->d_Vk[v]);
+  cudaFree(h->ocache);
   cudaFree(h->d_stats);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

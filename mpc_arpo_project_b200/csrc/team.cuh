@@ -24,6 +24,9 @@
 #include "common.cuh"
 #include "sim.cuh"
 
+#ifndef TEAM_OPC
+#define TEAM_OPC 3             // operators kept per team in the L2 cache (TeamArgs::ocache)
+#endif
 #ifndef TEAM_TM_CHUNK
 #define TEAM_TM_CHUNK 8        // TMEM columns per tcgen05.ld in the mat-vec (8 or 16)
 #endif
@@ -116,6 +119,10 @@ struct TeamArgs {
   double *scache;            // [B][SCACHE_CHUNKS][NCT] double2, or nullptr
   double *scache_rho;        // [B] rho the cached S was built for (< 0: empty)
   int *scache_var;           // [B]
+  // per-TEAM operator cache (whole-loop modes): the last TEAM_OPC operators this team built, [grid][TEAM_OPC][chunks][NCT]
+  // double2 in global memory (L2-resident).  Trajectories flip between velocity-sign variants at unchanged rho (95 % of the
+  // rebuilds of config 4); a flip back costs a 64-231 KB reload instead of the n^3 rebuild.
+  double *ocache;
   // results
   int *queue;                // [1] next lane
   unsigned long long *tot;   // [0] admm iterations, [1] qp solves, [2] operator rebuilds
@@ -555,6 +562,52 @@ __device__ __forceinline__ void tmem_wait_ld4(uint32_t (&r)[4]) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
 
+
+// S between tensor memory and a cache slot in global memory ([chunk][thread] double2: coalesced both ways).  Kept out of
+// line: inlined into the solve loop they cost the hot path registers (config 2 ran 4 % slower).
+template <int HALF, int NCT>
+__device__ __noinline__ void tm_load_operator(uint32_t taddr, const double2 *src) {
+  constexpr int SCHUNKS = HALF / 2;
+#pragma unroll
+  for (int g = 0; g < (2 * HALF) / 16; ++g) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 v = __ldcs(src + (size_t)(4 * g + j) * NCT);
+      w[4 * j] = (uint32_t)__double2loint(v.x); w[4 * j + 1] = (uint32_t)__double2hiint(v.x);
+      w[4 * j + 2] = (uint32_t)__double2loint(v.y); w[4 * j + 3] = (uint32_t)__double2hiint(v.y);
+    }
+    tmem_st16(taddr + 16 * g, w);
+  }
+#pragma unroll
+  for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
+    const double2 v = __ldcs(src + (size_t)c * NCT);
+    const uint32_t w4[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y),
+                            (uint32_t)__double2hiint(v.y)};
+    tmem_st4(taddr + 4 * c, w4);
+  }
+  tmem_wait_st();
+}
+template <int HALF, int NCT>
+__device__ __noinline__ void tm_store_operator(uint32_t taddr, double2 *dst) {
+  constexpr int SCHUNKS = HALF / 2;
+#pragma unroll
+  for (int g = 0; g < (2 * HALF) / 16; ++g) {
+    uint32_t w[16];
+    tmem_ld16(taddr + 16 * g, w);
+    tmem_wait_ld1(w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) __stcs(dst + (size_t)(4 * g + j) * NCT, make_double2(u2d(w[4 * j], w[4 * j + 1]), u2d(w[4 * j + 2], w[4 * j + 3])));
+  }
+#pragma unroll
+  for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
+    uint32_t w4[4];
+    tmem_ld4(taddr + 4 * c, w4);
+    tmem_wait_ld4(w4);
+    __stcs(dst + (size_t)c * NCT, make_double2(u2d(w4[0], w4[1]), u2d(w4[2], w4[3])));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // N variables, M rows (M <= 256, 2N <= 256); WA (<= 8), WAT2 (<= 8, entry PAIRS), WP are the maximum
 // ELL widths the instantiation supports.  Of the HALF entries of S a thread owns, the last SS live in
@@ -751,6 +804,15 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
   double op_rho = -1.0;                  // (rho, variant) the operator S currently held was built for: S depends on nothing
   int s_variant = -1;                    // else, so it survives from one lane to the next when both match
   constexpr int SCHUNKS = HALF / 2;      // double2 chunks of S per thread (operator cache layout [chunk][thread])
+  auto s_load = [&](const double2 *src) { if constexpr (TM) tm_load_operator<HALF, NCT>(taddr, src); };     // col_warp threads,
+  auto s_store = [&](double2 *dst) { if constexpr (TM) tm_store_operator<HALF, NCT>(taddr, dst); };         // pointer offset by tid
+  // Compiled in for the larger families only: at n = 81 a rebuild costs about one solve, flips at unchanged rho are 5 % of
+  // config 2's rebuilds, and the extra code cost the hot loop 2 %.
+  constexpr bool OC = TM && N > 100;
+  __shared__ double s_oc_rho[TEAM_OPC];      // tags of the team's operator cache (rho < 0: empty), written by thread 0
+  __shared__ int s_oc_var[TEAM_OPC], s_oc_next;
+  if (tid < TEAM_OPC) { s_oc_rho[tid] = -1.0; s_oc_var[tid] = -1; }
+  if (tid == 0) s_oc_next = 0;
   unsigned long long my_iters = 0, my_rebuilds = 0;
   TP_DECL
 
@@ -790,28 +852,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
     __syncthreads();
     if (TM && a.scache && (L.rho != op_rho || L.variant != s_variant) && L.c_rho == L.rho && L.c_var == L.variant) {
       // this lane's operator is in its cache slot: HBM -> registers -> tensor memory
-      if (col_warp) {
-        const double2 *src = reinterpret_cast<const double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid;
-#pragma unroll
-        for (int g = 0; g < (2 * HALF) / 16; ++g) {
-          uint32_t w[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double2 v = __ldcs(src + (size_t)(4 * g + j) * NCT);
-            w[4 * j] = (uint32_t)__double2loint(v.x); w[4 * j + 1] = (uint32_t)__double2hiint(v.x);
-            w[4 * j + 2] = (uint32_t)__double2loint(v.y); w[4 * j + 3] = (uint32_t)__double2hiint(v.y);
-          }
-          tmem_st16(taddr + 16 * g, w);
-        }
-#pragma unroll
-        for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
-          const double2 v = __ldcs(src + (size_t)c * NCT);
-          const uint32_t w4[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y),
-                                  (uint32_t)__double2hiint(v.y)};
-          tmem_st4(taddr + 4 * c, w4);
-        }
-        tmem_wait_st();
-      }
+      if (col_warp) s_load(reinterpret_cast<const double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid);
       op_rho = L.rho;
       s_variant = L.variant;
     }
@@ -854,6 +895,39 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
 
       // =============================== one solve ===============================
       while (st == -10) {
+        int oc_hit = -1;
+        if (OC && need_op && a.ocache) {
+          // A sign-variant flip at unchanged rho tends to flip back (95 % of config 4's rebuilds): park the OUTGOING
+          // operator before it is overwritten, unless the cache has it already.  Operators replaced because rho adapted are
+          // not parked (they rarely return, and config 2 would pay a 64 KB store per rebuild for a 5 % hit rate).
+          if (op_rho == rho && s_variant != variant && s_variant >= 0) {
+            bool have = false;
+#pragma unroll
+            for (int q = 0; q < TEAM_OPC; ++q) have = have || (s_oc_rho[q] == op_rho && s_oc_var[q] == s_variant);
+            const int victim = s_oc_next;
+            __syncthreads();
+            if (!have) {
+              if (col_warp)
+                s_store(reinterpret_cast<double2 *>(a.ocache) + ((size_t)blockIdx.x * TEAM_OPC + victim) * (SCHUNKS * NCT) + tid);
+              if (tid == 0) {
+                s_oc_rho[victim] = op_rho;
+                s_oc_var[victim] = s_variant;
+                s_oc_next = (victim + 1) % TEAM_OPC;
+              }
+            }
+            __syncthreads();
+          }
+#pragma unroll
+          for (int q = 0; q < TEAM_OPC; ++q)
+            if (s_oc_rho[q] == rho && s_oc_var[q] == variant) oc_hit = q;
+        }
+        if (need_op && oc_hit >= 0) {    // one of the team's last operators: reload it (bit-identical to a rebuild)
+          if (col_warp)
+            s_load(reinterpret_cast<const double2 *>(a.ocache) + ((size_t)blockIdx.x * TEAM_OPC + oc_hit) * (SCHUNKS * NCT) + tid);
+          op_rho = rho;
+          s_variant = variant;
+          need_op = false;
+        }
         if (need_op) {                   // S = V diag(1/(1+rho*lam)) V'
           if (tid < N) dk[tid] = 1.0 / (1.0 + rho * a.lam[variant * N + tid]);
           __syncthreads();
@@ -1187,24 +1261,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
       const bool put = a.list && a.scache && op_rho >= 0.0 && (L.c_rho != op_rho || L.c_var != s_variant);
       __syncthreads();
       if (put) {
-        if (col_warp) {
-          double2 *dst = reinterpret_cast<double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid;
-#pragma unroll
-          for (int g = 0; g < (2 * HALF) / 16; ++g) {
-            uint32_t w[16];
-            tmem_ld16(taddr + 16 * g, w);
-            tmem_wait_ld1(w);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) __stcs(dst + (size_t)(4 * g + j) * NCT, make_double2(u2d(w[4 * j], w[4 * j + 1]), u2d(w[4 * j + 2], w[4 * j + 3])));
-          }
-#pragma unroll
-          for (int c = 4 * ((2 * HALF) / 16); c < SCHUNKS; ++c) {
-            uint32_t w4[4];
-            tmem_ld4(taddr + 4 * c, w4);
-            tmem_wait_ld4(w4);
-            __stcs(dst + (size_t)c * NCT, make_double2(u2d(w4[0], w4[1]), u2d(w4[2], w4[3])));
-          }
-        }
+        if (col_warp) s_store(reinterpret_cast<double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid);
         if (tid == 0) { L.c_rho = op_rho; L.c_var = s_variant; }
       }
     }
