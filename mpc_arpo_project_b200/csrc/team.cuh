@@ -936,35 +936,38 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
             // order over k is the register version's, so S is bit-identical to it
             if (col_warp) {
               const double *Vk = a.Vk[variant];
+              // RB entries of the half row per pass: 16 at two teams per SM (128 registers), 32 with a whole SM's registers --
+              // V (211 KB per variant at n = 161) comes from L2, so fewer, fatter passes mean more loads in flight
+              constexpr int RB = (CT == 1) ? 32 : 16;
+              constexpr int NPASS = (HALF + RB - 1) / RB;
 #pragma unroll 1
-              constexpr int NPASS = (HALF + 15) / 16;
               for (int pass = 0; pass < NPASS; ++pass) {
-                double T[16];
+                double T[RB];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) T[j] = 0.0;
-                const int cnt2 = (pass < NPASS - 1) ? 8 : (HALF - 16 * (NPASS - 1)) / 2;
+                for (int j = 0; j < RB; ++j) T[j] = 0.0;
+                const int cnt2 = (pass < NPASS - 1) ? RB / 2 : (HALF - RB * (NPASS - 1)) / 2;
 #pragma unroll 3
                 for (int k = 0; k < N; ++k) {
                   const double *vrow = Vk + (size_t)k * NP2;
                   const double tk = has_col ? __ldg(vrow + col) * dk[k] : 0.0;
-                  const double2 *r2 = reinterpret_cast<const double2 *>(vrow + half * HALF + 16 * pass);
+                  const double2 *r2 = reinterpret_cast<const double2 *>(vrow + half * HALF + RB * pass);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
+                  for (int j = 0; j < RB / 2; ++j)
                     if (j < cnt2) {
                       const double2 vv = __ldg(r2 + j);
                       T[2 * j] = fma(tk, vv.x, T[2 * j]);
                       T[2 * j + 1] = fma(tk, vv.y, T[2 * j + 1]);
                     }
                 }
-                uint32_t w[16];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
+                for (int hh = 0; hh < RB / 8; ++hh) {
+                  uint32_t w[16];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     w[2 * j] = (uint32_t)__double2loint(T[8 * hh + j]);
                     w[2 * j + 1] = (uint32_t)__double2hiint(T[8 * hh + j]);
                   }
-                  const int c0 = 32 * pass + 16 * hh;               // first column of these 8 doubles
+                  const int c0 = 2 * RB * pass + 16 * hh;            // first column of these 8 doubles
                   if (c0 + 16 <= 2 * HALF) tmem_st16(taddr + c0, w);
                   else if (c0 < 2 * HALF) {                          // tail: 2*HALF - c0 columns, in 4-column pieces
 #pragma unroll
