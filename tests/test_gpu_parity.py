@@ -497,6 +497,22 @@ def test_results_are_reproducible_run_to_run():
             assert np.array_equal(r.ctrl_hist, runs[0].ctrl_hist, equal_nan=True)
 
 
+def test_operator_cache_does_not_change_results(monkeypatch):
+    """In-track delta-v lanes flip their velocity-sign variant at unchanged rho all the time (config 4): the Nx = 20 team
+    kernel then reloads parked operators from its L2 cache instead of rebuilding them.  A reloaded operator is the rebuilt
+    one bit for bit, so the run with the cache disabled must give identical telemetry."""
+    case = dict(Nx=20, inTrack=True, isDeltaV=True, isReject=False, sigma=None, T_final=40)
+    B = 64
+    x0, rng = lanes(case, B, 31)
+    sc, mp, fp, _ = make_params(M, case)
+    a = M.trajectorySimulateBatch(sc, mp, fp, None, x0, None)
+    monkeypatch.setenv("MPCB_NO_OCACHE", "1")
+    b = M.trajectorySimulateBatch(sc, mp, fp, None, x0, None)
+    assert a.stats["qp_solves"] == b.stats["qp_solves"] and a.stats["admm_iterations"] == b.stats["admm_iterations"]
+    np.testing.assert_array_equal(a.iters, b.iters)
+    assert np.array_equal(a.x_true, b.x_true, equal_nan=True) and np.array_equal(a.ctrl_hist, b.ctrl_hist, equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------ Monte-Carlo drivers
 def test_monte_carlo_reductions_match_per_lane_results():
     """disturbRejComp / success_rates_test as batched calls: the device-side statistics equal what the
