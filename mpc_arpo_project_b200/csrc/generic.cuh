@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
   int *ctype = reinterpret_cast<int *>(take((m + 1) / 2 + 1));
   GenLane &L = *reinterpret_cast<GenLane *>(p);
   __shared__ int s_lane;
-  __shared__ double s_c, s_tmp;
+  __shared__ double s_c;
   double *S = a.scratch + (size_t)blockIdx.x * n * n;
 
   auto team_max = [&](double val) -> double {
