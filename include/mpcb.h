@@ -16,7 +16,11 @@
  *     handle are serialised on its CUDA stream;
  *   - batch arrays are double precision, structure-of-arrays "[field][B]" (lane index fastest);
  *   - `io_on_device` != 0: the batch pointers are device pointers on the handle's GPU;
- *     `io_on_device` == 0: they are host pointers and the call copies in/out itself.
+ *     `io_on_device` == 0: they are host pointers and the call copies in/out itself;
+ *   - stream contract: the handle works on its own stream (mpcb_stream).  Every call returns after that stream
+ *     has drained, so outputs are complete on return.  INPUTS passed as device pointers must be complete before
+ *     the call: either synchronise the producing stream, or call mpcb_wait_stream(h, producer) first, which makes the
+ *     handle's stream wait (on the device, no host block) for everything enqueued on `producer` so far.
  */
 #ifndef MPCB_H
 #define MPCB_H
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MPCB_ABI_VERSION 3
+#define MPCB_ABI_VERSION 4
 
 typedef enum mpcb_status {
   MPCB_OK = 0,
@@ -113,6 +117,8 @@ typedef struct mpcb_sim_out {
   double *x_true_sub;    /* [4][NS][B]  xtrueP */
   double *ctrl_sub;      /* [2][NS][B]  ctrls */
   uint8_t *ctrlr_sub;    /* [NS][B]     controllerSeq codes 0/1/2 */
+  /* solver telemetry beyond the reference's SimRun (ABI 4) */
+  double *rho;           /* [T1-1][B]  the lane's ADMM step size after solve i (OSQP's adaptive rho; NaN = not reached) */
 } mpcb_sim_out;
 
 /* Run counters filled by the simulate / qp_solve calls (for bench.py's gpu_launches etc.). */
@@ -141,6 +147,10 @@ int mpcb_set_timing(mpcb_handle *h, int enable_kernel_timing);
 int mpcb_get_counters(mpcb_handle *h, mpcb_counters *out);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with events. */
 void *mpcb_stream(mpcb_handle *h);
+/* Order the handle's stream after everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the legacy
+ * default stream): cudaEventRecord + cudaStreamWaitEvent, no host synchronisation.  Call it before passing device
+ * pointers whose contents are still being produced on another stream (see the stream contract above). */
+int mpcb_wait_stream(mpcb_handle *h, void *producer_stream);
 
 /* prob.update(l,u); prob.update(Ax,l,u); res = prob.solve()  (:340-348, :296) for every lane:
  * xhat[6][B] is the estimate the bounds / signs are rebuilt from (simhelpers.py:66-67,124,137);
@@ -182,6 +192,12 @@ int mpcb_simulate_continuous(mpcb_handle *h, int64_t B, int32_t n_sub_total, int
  * all-reduce (sum) over NCCL. */
 #define MPCB_NSTATS 10
 int mpcb_stats(mpcb_handle *h, int64_t B, double *stats, int io_on_device);
+/* The one collective of a multi-GPU Monte-Carlo run: sum the MPCB_NSTATS statistics of the last simulation
+ * over the ranks of `nccl_comm` (an ncclComm_t the caller created with one rank per GPU), on the handle's stream, and
+ * return the global vector in stats (host pointer).  libnccl.so.2 is resolved at run time (dlopen): single-GPU users
+ * need no NCCL.  The reductions are sums of per-rank values that are themselves fixed-order sums, so the result does not
+ * depend on timing. */
+int mpcb_allreduce_stats(mpcb_handle *h, void *nccl_comm, double *stats);
 
 /* Disturbance draws on the device: noise[n_refresh][2][B] = (sigma_x, sigma_y) .* N(0,1) from Philox4x32-10, one block per
  * (lane + lane_offset, refresh), key = seed -- the reference's model `sigMat @ random.normal(0,1,4)` per noise_length steps

@@ -50,6 +50,7 @@ class MpcbSimOut(C.Structure):
         ("ctrlr_seq", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p), ("u_raw", C.c_void_p),
         ("ukf_clamped", C.c_void_p),
         ("x_true_sub", C.c_void_p), ("ctrl_sub", C.c_void_p), ("ctrlr_sub", C.c_void_p),
+        ("rho", C.c_void_p),
     ]
 
 
@@ -73,6 +74,7 @@ SYMBOLS = {
     "mpcb_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mpcb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(MpcbCounters)]),
     "mpcb_stream": (C.c_void_p, [C.c_void_p]),
+    "mpcb_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mpcb_qp_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mpcb_qp_get_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpcb_ukf_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -83,12 +85,13 @@ SYMBOLS = {
     "mpcb_simulate_continuous": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_int32, C.POINTER(MpcbSimOut), C.c_int]),
     "mpcb_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "mpcb_allreduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpcb_noise_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_void_p,
                                   C.c_void_p, C.c_int]),
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NSTATS = 10
 _lib = None
 

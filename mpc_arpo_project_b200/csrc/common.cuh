@@ -74,6 +74,8 @@ struct SimOutDev {
   int32_t *i_term; int32_t *is_success; int32_t *ukf_clamped; double *final_dist;
   double *x_true, *x_est, *ctrl; uint8_t *ctrlr_seq; int8_t *status; int16_t *iters; double *u_raw;
   double *x_true_sub, *ctrl_sub; uint8_t *ctrlr_sub;   // continuous simulator, every substep: [.][NS][B]
+  double *rho_hist;         // [T1-1][B] rho after solve i
+  double *fd_all;           // [B] internal: every lane's final distance (NaN -> 0), summed in a fixed order by stats_fd_kernel
   int T1, NS;
 };
 
@@ -99,6 +101,33 @@ struct PostArgs {
   int *list_next;           // [4][B]
   unsigned long long *solves_total;
 };
+
+// sum final_dist and final_dist^2 over the batch in an order that depends on B only (one block, strided partial sums, fixed
+// tree): run-to-run identical, unlike atomicAdd(double) from the lanes as they finish.  The other statistics are integer
+// counts, whose double sums are exact in any order.
+__global__ void __launch_bounds__(1024) stats_fd_kernel(const double *__restrict__ fd, int B, double *__restrict__ stats) {
+  __shared__ double s0[1024], s1[1024];
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = threadIdx.x; i < B; i += 1024) {
+    const double f = fd[i];
+    a0 += f;
+    a1 += f * f;
+  }
+  s0[threadIdx.x] = a0;
+  s1[threadIdx.x] = a1;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      s0[threadIdx.x] += s0[threadIdx.x + w];
+      s1[threadIdx.x] += s1[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = s0[0];
+    stats[1] = s1[0];
+  }
+}
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll

@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           L.nsolve += 1;
           if (a.out.status) a.out.status[(size_t)i * B + ln] = (int8_t)st;
           if (a.out.iters) a.out.iters[(size_t)i * B + ln] = (int16_t)iter;
+          if (a.out.rho_hist) a.out.rho_hist[(size_t)i * B + ln] = L.rho;
           if (a.out.ctrlr_seq) a.out.ctrlr_seq[(size_t)i * B + ln] = (uint8_t)code;
           if (a.out.u_raw) {
             a.out.u_raw[((size_t)0 * (T1 - 1) + i) * B + ln] = uraw[0];
@@ -616,8 +617,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         if (a.out.final_dist) a.out.final_dist[ln] = fd;
         if (a.out.ukf_clamped) a.out.ukf_clamped[ln] = L.ukf_clamp;
         const double f = (fd == fd) ? fd : 0.0;
-        atomicAdd(&a.stats[0], f);
-        atomicAdd(&a.stats[1], f * f);
+        if (a.out.fd_all) a.out.fd_all[ln] = f;   // stats[0], stats[1]: fixed-order sum afterwards (stats_fd_kernel)
         if (L.succ) atomicAdd(&a.stats[2], 1.0);
         atomicAdd(&a.stats[3], 1.0);
         atomicAdd(&a.stats[4], (double)L.iterm);

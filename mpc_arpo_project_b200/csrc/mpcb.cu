@@ -17,6 +17,14 @@
 #include "generic.cuh"
 #include "tile.cuh"
 #include <stdlib.h>
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX ranges around the entry points: visible in Nsight Systems timelines, free otherwise
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -133,6 +141,7 @@ struct mpcb_handle {
   int *list = nullptr;   // [2][4][B]
   LaneSim ls;
   double *lane_f64 = nullptr;   // backing store of LaneSim doubles
+  double *lane_fd = nullptr;    // [B] final distance of every lane (fixed-order statistics)
   int *lane_i32 = nullptr;      // backing store of LaneSim ints
   unsigned long long *d_tot = nullptr;   // [0] admm iterations, [1] qp solves, [2] operator rebuilds, [3] spare
   double *d_stats = nullptr;             // [MPCB_NSTATS]
@@ -142,7 +151,7 @@ struct mpcb_handle {
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_wait = nullptr;
   mpcb_counters ctr;
 };
 
@@ -785,6 +794,20 @@ static int launch_generic(mpcb_handle *h, GenArgs &g) {
 extern "C" int mpcb_abi_version(void) { return MPCB_ABI_VERSION; }
 extern "C" const char *mpcb_last_error(void) { return g_err.c_str(); }
 
+static int create_tail(mpcb_handle *h, bool debris) {
+  if (!debris) CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&h->d_tot, 16 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_tot, 0, 16 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_queue, sizeof(int)));
+  CK(cudaMalloc(&h->d_stats, 2 * MPCB_NSTATS * sizeof(double)));
+  CK(cudaMallocHost(&h->h_cnt, 8 * sizeof(int)));
+  CK(cudaEventCreate(&h->ev_t0));
+  CK(cudaEventCreate(&h->ev_t1));
+  CK(cudaEventCreateWithFlags(&h->ev_wait, cudaEventDisableTiming));
+  return MPCB_OK;
+}
+
 extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out) {
   if (!pr || !out) return fail(MPCB_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -804,6 +827,7 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
   if (pr->check_termination < 1 || pr->max_iter % pr->check_termination != 0 ||
       (pr->adaptive_rho && (pr->adaptive_rho_interval < 1 || pr->adaptive_rho_interval % pr->check_termination != 0)))
     return fail(MPCB_ERR_INVALID, "max_iter and adaptive_rho_interval must be multiples of check_termination");
+  if (pr->max_iter > INT16_MAX) return fail(MPCB_ERR_INVALID, "max_iter above 32767: the per-solve iteration telemetry is int16");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(MPCB_ERR_INVALID, "no such CUDA device");
@@ -867,15 +891,13 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
     mpcb_destroy(h);
     return rc;
   }
-  if (!debris) CK(cudaFuncSetAttribute((const void *)h->kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&h->d_tot, 16 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->d_tot, 0, 16 * sizeof(unsigned long long)));
-  CK(cudaMalloc(&h->d_queue, sizeof(int)));
-  CK(cudaMalloc(&h->d_stats, MPCB_NSTATS * sizeof(double)));
-  CK(cudaMallocHost(&h->h_cnt, 8 * sizeof(int)));
-  CK(cudaEventCreate(&h->ev_t0));
-  CK(cudaEventCreate(&h->ev_t1));
+  rc = create_tail(h, debris);       // a failure past this point still owns h: release it through mpcb_destroy
+  if (rc != MPCB_OK) {
+    const std::string keep = g_err;
+    mpcb_destroy(h);
+    g_err = keep;
+    return rc;
+  }
   *out = h;
   return MPCB_OK;
 }
@@ -885,7 +907,8 @@ static void free_batch(mpcb_handle *h) {
   h->scache = h->scache_rho = nullptr; h->scache_var = nullptr; h->scache_tried = false;
   cudaFree(h->xs); cudaFree(h->zs); cudaFree(h->ys); cudaFree(h->rho); cudaFree(h->par); cudaFree(h->u0);
   cudaFree(h->iter); cudaFree(h->status); cudaFree(h->flip); cudaFree(h->lane_state); cudaFree(h->cnt);
-  cudaFree(h->list); cudaFree(h->lane_f64); cudaFree(h->lane_i32);
+  cudaFree(h->list); cudaFree(h->lane_f64); cudaFree(h->lane_i32); cudaFree(h->lane_fd);
+  h->lane_fd = nullptr;
   h->xs = h->zs = h->ys = h->rho = h->par = h->u0 = h->lane_f64 = nullptr;
   h->iter = h->status = h->flip = h->cnt = h->list = h->lane_i32 = nullptr;
   h->lane_state = nullptr;
@@ -916,6 +939,7 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->ev_wait) cudaEventDestroy(h->ev_wait);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MPCB_OK;
@@ -958,6 +982,7 @@ extern "C" int mpcb_batch_alloc(mpcb_handle *h, int64_t B) {
     // LaneSim: doubles 4+6+36+4+2+2+1+2+4 = 61 per lane, ints 7 per lane
     CK(cudaMalloc(&h->lane_f64, (size_t)B * 61 * 8));
     CK(cudaMalloc(&h->lane_i32, (size_t)B * 7 * 4));
+    CK(cudaMalloc(&h->lane_fd, (size_t)B * 8));
     double *d = h->lane_f64;
     LaneSim &ls = h->ls;
     ls.xtrue = d; d += 4 * B;
@@ -997,6 +1022,14 @@ extern "C" int mpcb_get_counters(mpcb_handle *h, mpcb_counters *out) {
 }
 
 extern "C" void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int mpcb_wait_stream(mpcb_handle *h, void *producer_stream) {
+  if (!h) return fail(MPCB_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev_wait, (cudaStream_t)producer_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_wait, 0));
+  return MPCB_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 static void fill_args(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int mode) {
@@ -1226,6 +1259,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
   if (!h || !xhat) return fail(MPCB_ERR_INVALID, "null argument");
   if (h->B == 0 || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_batch_alloc(B) must precede mpcb_qp_solve with the same B");
   CK(cudaSetDevice(h->device));
+  NvtxRange nvtx_("mpcb_qp_solve");
   Stage st(&h->stage_pool);
   const double *d_xhat;
   double *d_u0;
@@ -1350,6 +1384,19 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   if (h->B == 0 || B != h->B) return fail(MPCB_ERR_STATE, "mpcb_batch_alloc(B) must precede a simulation with the same B");
   if (nsteps < 0) return fail(MPCB_ERR_INVALID, "negative step count");
   if (h->sc.has_noise && (!noise || n_refresh < 1)) return fail(MPCB_ERR_INVALID, "has_noise problems need a noise tensor");
+  if (h->sc.has_noise) {
+    // the reference redraws every noise_length steps (trajectorySimulate.py:351-353; per noise_hold_sub substeps in
+    // trajectorySimulateC.py:296-307): a tensor with fewer rows would silently reuse its last draw
+    const int64_t need = (mode == MODE_CONTINUOUS)
+                             ? (n_sub_total > 0 ? (int64_t)(n_sub_total - 1) / std::max(1, noise_hold_sub) + 1 : 1)
+                             : (int64_t)nsteps / h->sc.noise_length + 1;
+    if (n_refresh < need) {
+      char b[160];
+      snprintf(b, sizeof b, "noise tensor has %d rows, the run consumes %lld (one per hold interval)", n_refresh, (long long)need);
+      return fail(MPCB_ERR_INVALID, b);
+    }
+  }
+  NvtxRange nvtx_(mode == MODE_CONTINUOUS ? "mpcb_simulate_continuous" : "mpcb_simulate_discrete");
   CK(cudaSetDevice(h->device));
   RC(mpcb_batch_alloc(h, B));   // cold start: x = z = y = 0, rho = rho0 (a fresh osqp.setup, :242-245)
   static const mpcb_sim_out none = {};
@@ -1373,6 +1420,8 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   RC(st.out(o.iters, (T1 - 1) * B, io_on_device, &od.iters));
   RC(st.out(o.u_raw, 2 * (T1 - 1) * B, io_on_device, &od.u_raw));
   RC(st.out(o.ukf_clamped, (size_t)B, io_on_device, &od.ukf_clamped));
+  RC(st.out(o.rho, (T1 - 1) * B, io_on_device, &od.rho_hist));
+  od.fd_all = h->lane_fd;
   const size_t NS = (mode == MODE_CONTINUOUS) ? (size_t)n_sub_total : 0;
   od.NS = (int)NS;
   if (mode == MODE_CONTINUOUS) {
@@ -1392,6 +1441,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   if (od.ctrlr_seq) CK(cudaMemsetAsync(od.ctrlr_seq, 0, (T1 - 1) * B, h->stream));
   if (od.status) CK(cudaMemsetAsync(od.status, 0, (T1 - 1) * B, h->stream));
   if (od.iters) CK(cudaMemsetAsync(od.iters, 0, (T1 - 1) * B * 2, h->stream));
+  if (od.rho_hist) CK(cudaMemsetAsync(od.rho_hist, 0xff, (T1 - 1) * B * 8, h->stream));
 
   AdmmArgs aa;
   PostArgs pa;
@@ -1443,6 +1493,9 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;
   }
+  stats_fd_kernel<<<1, 1024, 0, h->stream>>>(h->lane_fd, (int)B, h->d_stats);
+  CK(cudaGetLastError());
+  h->ctr.kernel_launches += 1;
   CK(cudaEventRecord(h->ev_t1, h->stream));
   RC(st.back(o.i_term, od.i_term, (size_t)B, io_on_device, h->stream));
   RC(st.back(o.is_success, od.is_success, (size_t)B, io_on_device, h->stream));
@@ -1455,6 +1508,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
   RC(st.back(o.iters, od.iters, (T1 - 1) * B, io_on_device, h->stream));
   RC(st.back(o.u_raw, od.u_raw, 2 * (T1 - 1) * B, io_on_device, h->stream));
   RC(st.back(o.ukf_clamped, od.ukf_clamped, (size_t)B, io_on_device, h->stream));
+  RC(st.back(o.rho, od.rho_hist, (T1 - 1) * B, io_on_device, h->stream));
   if (mode == MODE_CONTINUOUS) {
     RC(st.back(o.x_true_sub, od.x_true_sub, 4 * NS * B, io_on_device, h->stream));
     RC(st.back(o.ctrl_sub, od.ctrl_sub, 2 * NS * B, io_on_device, h->stream));
@@ -1504,6 +1558,44 @@ extern "C" int mpcb_noise_fill(mpcb_handle *h, int64_t B, int32_t n_refresh, dou
   h->ctr.kernel_launches += 1;
   RC(st.back(noise, d_noise, (size_t)n_refresh * 2 * B, io_on_device, h->stream));
   if (raw) RC(st.back(raw, d_raw, (size_t)n_refresh * 4 * B, io_on_device, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MPCB_OK;
+}
+
+// ncclAllReduce resolved at run time: libmpcb.so has no link-time NCCL dependency
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+static nccl_allreduce_fn resolve_nccl_allreduce() {
+  static nccl_allreduce_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");        // already loaded (e.g. by torch): use that copy
+    if (!sym) {
+      void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+      if (lib) sym = dlsym(lib, "ncclAllReduce");
+    }
+    fn = (nccl_allreduce_fn)sym;
+  }
+  return fn;
+}
+
+extern "C" int mpcb_allreduce_stats(mpcb_handle *h, void *nccl_comm, double *stats_out) {
+  if (!h || !nccl_comm || !stats_out) return fail(MPCB_ERR_INVALID, "null argument");
+  if (!h->sim_done) return fail(MPCB_ERR_STATE, "mpcb_allreduce_stats needs a finished simulation");
+  nccl_allreduce_fn ar = resolve_nccl_allreduce();
+  if (!ar) return fail(MPCB_ERR_STATE, "libnccl.so.2 not found (ncclAllReduce could not be resolved)");
+  CK(cudaSetDevice(h->device));
+  NvtxRange nvtx_("mpcb_allreduce_stats");
+  const double iters = (double)h->last_sim_iterations;
+  CK(cudaMemcpyAsync(h->d_stats + 6, &iters, 8, cudaMemcpyHostToDevice, h->stream));
+  const int rc = ar(h->d_stats, h->d_stats + MPCB_NSTATS, MPCB_NSTATS, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, h->stream);
+  if (rc != 0) {
+    char b[96];
+    snprintf(b, sizeof b, "ncclAllReduce failed with ncclResult_t %d", rc);
+    return fail(MPCB_ERR_CUDA, b);
+  }
+  CK(cudaMemcpyAsync(stats_out, h->d_stats + MPCB_NSTATS, MPCB_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return MPCB_OK;
 }

@@ -416,6 +416,7 @@ __global__ void post_kernel(const __grid_constant__ PostArgs a) {
       a.ls.nsolve[ln] += 1;
       if (a.out.status) a.out.status[(size_t)i * B + ln] = (int8_t)status;
       if (a.out.iters) a.out.iters[(size_t)i * B + ln] = (int16_t)a.iter[ln];
+      if (a.out.rho_hist) a.out.rho_hist[(size_t)i * B + ln] = a.rho[ln];
       if (a.out.ctrlr_seq) a.out.ctrlr_seq[(size_t)i * B + ln] = (uint8_t)code;
       if (a.out.u_raw) {
         a.out.u_raw[((size_t)0 * (T1 - 1) + i) * B + ln] = uraw[0];
@@ -544,8 +545,7 @@ __global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__re
     if (a.out.i_term) a.out.i_term[ln] = it;
     if (a.out.is_success) a.out.is_success[ln] = a.ls.succ[ln];
     if (a.out.final_dist) a.out.final_dist[ln] = fd;
-    v[0] = (fd == fd) ? fd : 0.0;
-    v[1] = v[0] * v[0];
+    if (a.out.fd_all) a.out.fd_all[ln] = (fd == fd) ? fd : 0.0;      // stats[0], stats[1]: fixed-order sum afterwards
     v[2] = a.ls.succ[ln];
     v[3] = 1.0;
     v[4] = it;
@@ -556,7 +556,7 @@ __global__ void finalize_kernel(const __grid_constant__ PostArgs a, double *__re
     if (it < ((a.mode == MODE_CONTINUOUS) ? a.n_sub_total : a.nsteps)) atomicAdd(&stats[9], 1.0);
   }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 2; k < 6; ++k) {                  // integer counts: exact in any order
     const double s = warp_sum(v[k]);
     if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(&stats[k], s);
   }

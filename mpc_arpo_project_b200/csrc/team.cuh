@@ -327,6 +327,7 @@ __device__ __noinline__ void lane_post_step(const TeamArgs &a, LaneCtx &L, UkfSc
     L.nsolve += 1;
     if (a.out.status) a.out.status[(size_t)i * B + ln] = (int8_t)L.status;
     if (a.out.iters) a.out.iters[(size_t)i * B + ln] = (int16_t)L.iter;
+    if (a.out.rho_hist) a.out.rho_hist[(size_t)i * B + ln] = L.rho;
     if (a.out.ctrlr_seq) a.out.ctrlr_seq[(size_t)i * B + ln] = (uint8_t)code;
     if (a.out.u_raw) {
       a.out.u_raw[((size_t)0 * (T1 - 1) + i) * B + ln] = uraw[0];
@@ -470,8 +471,7 @@ __device__ __noinline__ void lane_finalize(const TeamArgs &a, LaneCtx &L) {
   if (a.out.ukf_clamped) a.out.ukf_clamped[ln] = L.ukf_clamp;
   a.rho[ln] = L.rho;
   const double f = (fd == fd) ? fd : 0.0;
-  atomicAdd(&a.stats[0], f);
-  atomicAdd(&a.stats[1], f * f);
+  if (a.out.fd_all) a.out.fd_all[ln] = f;         // stats[0], stats[1]: summed in a fixed order afterwards (stats_fd_kernel)
   if (L.succ) atomicAdd(&a.stats[2], 1.0);
   atomicAdd(&a.stats[3], 1.0);
   atomicAdd(&a.stats[4], (double)L.iterm);

@@ -18,7 +18,7 @@ from . import _lib
 from .mpcsim import BatchSimRun
 from .problem import Problem
 
-_RECORD_ALL = ("x_true", "x_est", "ctrl", "ctrlr_seq", "status", "iters", "u_raw")
+_RECORD_ALL = ("x_true", "x_est", "ctrl", "ctrlr_seq", "status", "iters", "u_raw", "rho")
 
 
 def _is_torch(a) -> bool:
@@ -176,6 +176,7 @@ class Engine:
         if B != self.B:
             self.batch_alloc(B)
         ar = _Arrays(xhat, self.device)
+        self._order_after_caller(ar)
         u0, pu = ar.new((2, B))
         st, ps = ar.new((B,), np.int32)
         it, pi = ar.new((B,), np.int32)
@@ -192,6 +193,7 @@ class Engine:
         """``kf.predict(u); kf.update(z)`` on copies of ``x[6, B]``, ``P[36, B]``; returns the new (x, P)."""
         B = x.shape[1]
         ar = _Arrays(x, self.device)
+        self._order_after_caller(ar)
         x = x.clone() if ar.on_device else np.array(x, dtype=np.float64, order="C")
         P = P.clone() if ar.on_device else np.array(P, dtype=np.float64, order="C")
         _lib.check(self.lib.mpcb_ukf_step(self._h, B, ar.ptr(x, shape=(6, B)), ar.ptr(P, shape=(36, B)),
@@ -220,6 +222,7 @@ class Engine:
     def plant_lin_step(self, x, u, w=None):
         B = x.shape[1]
         ar = _Arrays(x, self.device)
+        self._order_after_caller(ar)
         x = x.clone() if ar.on_device else np.array(x, dtype=np.float64, order="C")
         _lib.check(self.lib.mpcb_plant_lin_step(self._h, B, ar.ptr(x, shape=(4, B)), ar.ptr(u, shape=(2, B)),
                                                 ar.ptr(w, shape=(2, B)) if w is not None else None, int(ar.on_device)))
@@ -228,6 +231,7 @@ class Engine:
     def plant_rk4(self, x, u, w, nsub: int, dt: float):
         B = x.shape[1]
         ar = _Arrays(x, self.device)
+        self._order_after_caller(ar)
         x = x.clone() if ar.on_device else np.array(x, dtype=np.float64, order="C")
         _lib.check(self.lib.mpcb_plant_rk4(self._h, B, ar.ptr(x, shape=(4, B)), ar.ptr(u, shape=(2, B)),
                                            ar.ptr(w, shape=(2, B)) if w is not None else None, int(nsub), float(dt),
@@ -243,7 +247,7 @@ class Engine:
             "ukf_clamped": ((B,), np.int32),
             "x_true": ((4, T1, B), np.float64), "x_est": ((6, T1, B), np.float64), "ctrl": ((2, T1, B), np.float64),
             "ctrlr_seq": ((T1 - 1, B), np.uint8), "status": ((T1 - 1, B), np.int8), "iters": ((T1 - 1, B), np.int16),
-            "u_raw": ((2, T1 - 1, B), np.float64),
+            "u_raw": ((2, T1 - 1, B), np.float64), "rho": ((T1 - 1, B), np.float64),
             "x_true_sub": ((4, NS, B), np.float64), "ctrl_sub": ((2, NS, B), np.float64), "ctrlr_sub": ((NS, B), np.uint8),
         }
         for name in ("i_term", "is_success", "final_dist", "ukf_clamped") + tuple(record):
@@ -261,17 +265,27 @@ class Engine:
         return BatchSimRun(i_term=res["i_term"], isSuccess=res["is_success"], final_dist=res["final_dist"],
                            x_true=res.get("x_true"), x_est=res.get("x_est"), ctrl_hist=res.get("ctrl"),
                            ctrlr_seq=res.get("ctrlr_seq"), status=res.get("status"), iters=res.get("iters"),
-                           u_raw=res.get("u_raw"), ukf_clamped=res["ukf_clamped"], x_true_sub=res.get("x_true_sub"),
+                           u_raw=res.get("u_raw"), rho=res.get("rho"), ukf_clamped=res["ukf_clamped"], x_true_sub=res.get("x_true_sub"),
                            ctrl_sub=res.get("ctrl_sub"), ctrlr_sub=res.get("ctrlr_sub"), stats=dict(zip(keys, stats.tolist())),
                            stats_vec=stats)
 
-    def simulate_discrete(self, x0, noise=None, nsteps: Optional[int] = None, record: Sequence[str] = _RECORD_ALL) -> BatchSimRun:
+    def _order_after_caller(self, ar: "_Arrays"):
+        """Device-pointer calls: order the engine's stream after torch's current stream, so inputs still being produced
+        by torch kernels are complete before the engine reads them (``mpcb_wait_stream``; stream contract in mpcb.h).
+        Outputs need no such step: every call returns after the engine's stream has drained."""
+        if ar.on_device:
+            import torch
+            _lib.check(self.lib.mpcb_wait_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def simulate_discrete(self, x0, noise, nsteps: int, record: Sequence[str] = _RECORD_ALL) -> BatchSimRun:
         """``trajectorySimulate`` for B lanes.  ``x0[4, B]``; ``noise[R, 2, B]`` sigma-scaled position
-        disturbances (row r is applied from step ``r*noise_length``); ``record`` selects telemetry."""
+        disturbances (row r is applied from step ``r*noise_length``; ``None`` for noise-free problems); ``nsteps``
+        control steps; ``record`` selects telemetry."""
         B = x0.shape[1]
         if B != self.B:
             self.batch_alloc(B)
         ar = _Arrays(x0, self.device, self._host_cache)
+        self._order_after_caller(ar)
         out, res = self._sim_outputs(ar, B, nsteps + 1, record)
         R = 0 if noise is None else noise.shape[0]
         _lib.check(self.lib.mpcb_simulate_discrete(self._h, B, int(nsteps), ar.ptr(x0, shape=(4, B)),
@@ -286,6 +300,7 @@ class Engine:
         if B != self.B:
             self.batch_alloc(B)
         ar = _Arrays(x0, self.device, self._host_cache)
+        self._order_after_caller(ar)
         T1 = n_sub_total // ratio + 1
         out, res = self._sim_outputs(ar, B, T1, record, int(n_sub_total))
         R = 0 if noise is None else noise.shape[0]

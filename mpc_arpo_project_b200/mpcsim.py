@@ -131,6 +131,7 @@ class BatchSimRun:
     status: Optional[np.ndarray] = None
     iters: Optional[np.ndarray] = None
     u_raw: Optional[np.ndarray] = None
+    rho: Optional[np.ndarray] = None             # [T-1, B] ADMM step size after each solve (record 'rho')
     ukf_clamped: Optional[np.ndarray] = None     # [B] 1 where the reference's UKF would have raised LinAlgError
     x_true_sub: Optional[np.ndarray] = None      # continuous simulator, every substep: [4, NS, B] (record 'x_true_sub')
     ctrl_sub: Optional[np.ndarray] = None        # [2, NS, B]

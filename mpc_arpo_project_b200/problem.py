@@ -259,6 +259,15 @@ def build_problem(sim_conditions, mpc_params, fail_params, debris=None,
         P[o:o + 2, o:o + 2] = Ru
         P[o + 2:o + 7, o + 2:o + 7] = Rs
     P[n - 2:, n - 2:] = np.eye(2)
+    # OSQP's check_termination also tests a DUAL-infeasibility certificate (osqp auxil.c is_dual_infeasible: q'dx < 0,
+    # ||P dx||_inf <= eps_dual_inf ||dx||_inf, A dx in the recession cone of [l, u]).  The device kernels do not carry it:
+    # P is positive definite for this problem family (Q, S, Ru, Rs, I_2 on the diagonal blocks), so
+    # ||P dx||_inf >= lam_min(P) ||dx||_inf / sqrt(n) and the certificate cannot hold while lam_min / sqrt(n) > eps_dual_inf.
+    # The premise is checked here rather than assumed (a semidefinite P must not silently run without the test).
+    lam_min_P = float(np.linalg.eigvalsh(0.5 * (P + P.T)).min())
+    if lam_min_P / np.sqrt(n) <= st.eps_dual_inf:
+        raise NotImplementedError(f"cost Hessian is not safely positive definite (lam_min = {lam_min_P:.3g}): the engine omits "
+                                  "OSQP's dual-infeasibility certificate, which this problem could trigger")
 
     A = np.zeros((m, n))
     l = np.full(m, -np.inf)

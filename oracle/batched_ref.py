@@ -31,7 +31,11 @@ def _ninf(a):
 class BatchedQP:
     """Shared tables + per-lane ADMM state for B lanes."""
 
-    def __init__(self, setup, B, settings=None):
+    def __init__(self, setup, B, settings=None, spectral=None):
+        """``spectral``: optional ``(V[4,n,n], lam[4,n])`` to use instead of this class's own generalised eigen-decomposition.
+        Two ``eigh`` calls on inputs that differ in the last bit reconstruct ``M(rho)^-1`` to 1e-11..1e-9 relative only (the
+        pencil has condition ~1e6), which is the largest difference between the engine and this oracle; passing the engine's
+        tables (``Problem.V, Problem.lam``, themselves checked in tests/test_problem.py) isolates the device arithmetic."""
         s = setup
         st = dict(DEFAULT_SETTINGS)
         st.update(settings or {})
@@ -65,7 +69,10 @@ class BatchedQP:
             Af, Ac = A[ct == -1], A[ct != -1]
             Bm = self.P + st['sigma'] * np.eye(self.n) + RHO_MIN * Af.T @ Af
             Gm = Ac.T @ (w[ct != -1][:, None] * Ac)
-            lam, V = sla.eigh(0.5 * (Gm + Gm.T), 0.5 * (Bm + Bm.T))
+            if spectral is None:
+                lam, V = sla.eigh(0.5 * (Gm + Gm.T), 0.5 * (Bm + Bm.T))
+            else:
+                V, lam = np.asarray(spectral[0][v], float), np.asarray(spectral[1][v], float)
             self.Av.append(A)
             self.V.append(V)
             self.lam.append(np.maximum(lam, 0))
@@ -195,7 +202,7 @@ class BatchedQP:
 
 
 def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=None, regen_sigmas=True, nsteps=None,
-                            chol_fail='raise'):
+                            chol_fail='raise', spectral=None):
     """Batched ``trajectorySimulate`` (debris-free).  ``x0_batch[B,4]``; ``noise_batch[R,2,B]``
     holds sigma-scaled position disturbances, refreshed every ``noise_length`` steps
     (R >= nsim//noise_length + 1).  Returns a dict of SoA arrays."""
@@ -204,7 +211,7 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
     sc0 = copy.copy(sc)
     s = build_setup(sc0, mp, fp, None)
     nsim = int(sc.T_final / sc.time_stp) if nsteps is None else nsteps
-    qp = BatchedQP(s, B, settings)
+    qp = BatchedQP(s, B, settings, spectral=spectral)
     qp.is_reject = 1.0 if sc.isReject else 0.0
     has_noise = sc.noise is not None
     nrep = s.noiseRepeat
@@ -216,6 +223,7 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
     status = np.zeros((nsim, B), int)
     iters = np.zeros((nsim, B), int)
     u_raw = np.full((nsim, B, 2), np.nan)
+    rho_hist = np.full((nsim, B), np.nan)          # rho each lane ended solve i with (parity reports: rho at a divergence)
     xtrue[0] = x0_batch
     xest[0, :, :4] = x0_batch
     xest[0, :, 4:] = 0
@@ -275,6 +283,7 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
             break
         sv, its = qp.solve(idx)
         status[i, idx], iters[i, idx] = sv, its
+        rho_hist[i, idx] = qp.rho[idx]
         xs = xe_store[idx, :4]
         solved = sv == OSQP_SOLVED
         xi = np.where(solved, 0.0, xintf[idx] + xs[:, 0] - s.xr[0])
@@ -321,4 +330,4 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
         if has_noise and (i + 1) % nrep == 0:
             noise[:, :2] = noise_batch[(i + 1) // nrep].T
     return dict(i_term=iterm, x_true=xtrue, x_est=xest, ctrl_hist=ctrls, ctrlr_seq=seq, status=status, iters=iters,
-                u_raw=u_raw, rho=qp.rho.copy(), flip_flag=qp.flip_flag.copy(), ukf_clamped=clamped)
+                u_raw=u_raw, rho=qp.rho.copy(), rho_hist=rho_hist, flip_flag=qp.flip_flag.copy(), ukf_clamped=clamped)

@@ -127,32 +127,10 @@ def import_reference(ref_root='/root/reference'):
 def make_params(M, case):
     """Parameter sets after test/traj_eval_radial.py:17-72, traj_eval_radialC.py:17-75,
     traj_eval_in_track.py:14-66 (u_lim supplied), disturbRejComp.py:17-72.  ``M`` is a
-    module exposing the mpcsim classes (the reference's or the product's)."""
-    Q = 8e+02 * sparse.diags([0.2 ** 2., 10 ** 2., 3.8 ** 2, 900.])
-    R = 1000 ** 2 * sparse.diags([1., 1.])
-    Rs = 5 ** 2 * sparse.eye(5)
-    v = 50000 * np.ones(5)
-    v[-2] = -v[-2]
-    v[-1] = 0
-    fp = M.FailsafeParams(0.005 * np.diag([0.0001, 1, 100000., 1., 0.01]), 100 * np.diag([1, 1]), np.eye(1, 4), np.zeros([2, 2]))
-    c = dict(case)
-    Nx = c.get('Nx', 10)
-    in_track = c.get('inTrack', False)
-    if in_track:
-        x0 = np.array(c.get('x0', [-10., 100., 0., 0.]))
-        xr = np.array([0., 2.5, 0., 0.])
-        Rs = 5 ** 2 * sparse.diags([1.5, 1.5, 1, 1, 1e5])
-        v[-1] = 1e-09
-    else:
-        x0 = np.array(c.get('x0', [100., 10., 0., 0.]))
-        xr = np.array([2.5, 0., 0., 0.])
-    noise = M.Noise((c['sigma'], c['sigma']), c.get('noise_length', 50)) if c.get('sigma') else None
-    sc = M.SimConditions(x0, xr, 2.5, 10 * (np.pi / 180), 1.5, 1.107e-3, 0.5, c.get('isReject', True), (0.2, 45), noise,
-                         in_track, T_cont=c.get('T_cont', float('nan')), T_final=c.get('T_final', 150),
-                         isDeltaV=c.get('isDeltaV', False))
-    mp = M.MPCParams(Q, R, Rs, v, {"Nx": Nx, "Nc": 5, "Nb": 5}, (0.2, 0.2), swap_xy=in_track)
-    debris = M.Debris(*c['debris']) if c.get('debris') else None
-    return sc, mp, fp, debris
+    module exposing the mpcsim classes (the reference's or the product's).  The literals live in the
+    package (``mpc_arpo_project_b200/presets.py``) so that product code never imports the oracle."""
+    from mpc_arpo_project_b200.presets import make_params as _mk
+    return _mk(case, M)
 
 
 CASES = {
