@@ -145,6 +145,10 @@ int mpcb_destroy(mpcb_handle *h);
 int mpcb_batch_alloc(mpcb_handle *h, int64_t B);
 int mpcb_set_timing(mpcb_handle *h, int enable_kernel_timing);
 int mpcb_get_counters(mpcb_handle *h, mpcb_counters *out);
+/* Which solver blocks this handle can run (bit mask): 1 = warp-per-lane block kernel, 2 = team kernel (whole closed loop per
+ * CTA), 4 = DMMA tile kernel, 8 = multi-RHS wave kernel (DMMA, unscaled sparse phases), 16 = per-lane debris kernel.
+ * MPCB_SOLVER = block | team | tile | wave forces one; tests use the mask to know that the forced block really ran. */
+int mpcb_solver_blocks(mpcb_handle *h);
 /* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with events. */
 void *mpcb_stream(mpcb_handle *h);
 /* Order the handle's stream after everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the legacy

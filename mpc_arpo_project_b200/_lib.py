@@ -74,6 +74,7 @@ SYMBOLS = {
     "mpcb_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mpcb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(MpcbCounters)]),
     "mpcb_stream": (C.c_void_p, [C.c_void_p]),
+    "mpcb_solver_blocks": (C.c_int, [C.c_void_p]),
     "mpcb_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mpcb_qp_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mpcb_qp_get_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

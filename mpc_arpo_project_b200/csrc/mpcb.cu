@@ -16,6 +16,7 @@
 #include "team.cuh"
 #include "generic.cuh"
 #include "tile.cuh"
+#include "wave.cuh"
 #include <stdlib.h>
 #include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>
@@ -125,6 +126,13 @@ struct mpcb_handle {
   size_t tile_smem = 0;
   int tile_warps = 4;
   int64_t tile_min_lanes = INT64_MAX;  // the tile kernel is opt-in (MPCB_SOLVER=tile): the team kernel is faster at every batch size measured so far
+  // wave kernel (multi-RHS DMMA, 8 lanes per warp, unscaled sparse phases): round-based solver block of the n = 81 family
+  bool wave_ok = false;
+  WaveHdr wave_hdr;
+  WaveConst wave_k;
+  unsigned char *d_wave_blob[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t wave_smem = 0;
+  int64_t wave_min_lanes = 16384;      // default solver block of the round-based simulators from this batch size on
   // per-lane path (debris lanes)
   bool generic_ok = false;
   GenArgs gproto;
@@ -680,6 +688,190 @@ static int build_tile_tables(mpcb_handle *h) {
   return MPCB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Wave kernel tables (wave.cuh): Vp = D V in GEMM-position order per sign variant, [slot][quad member] scaling tables, and
+// the unscaled block coefficients (Ad, Ad - Bd K, Bd, C, V_ecr, weights) the kernel uses as constants.  The coefficients
+// are READ OFF the unscaled A / P the caller passed and A is then rebuilt from them: any mismatch (another problem
+// structure) leaves wave_ok false and the other solver blocks take the batch.
+static int build_wave_tables(mpcb_handle *h) {
+  const HostProblem &hp = h->hp;
+  const mpcb_problem &p = hp.p;
+  const int n = p.n, m = p.m, NX = WAVE_NX, NC = WAVE_NC, NB = WAVE_NB;
+  if (n != WAVE_N || m != WAVE_M || p.Nx != NX || p.Nc != NC || p.Nb != NB || hp.A_u.empty() || getenv("MPCB_NO_WAVE")) return MPCB_OK;
+  const int nX = 4 * (NX + 1), RB = nX + 5 * (NX + 1);
+  const std::vector<double> &A = hp.A_u, &P = hp.P_u;
+  auto Aat = [&](int r, int c) { return A[(size_t)r * n + c]; };
+  auto Pat = [&](int r, int c) { return P[(size_t)r * n + c]; };
+  WaveConst K;
+  memset(&K, 0, sizeof K);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      K.Ad[4 * i + j] = Aat(4 + i, j);
+      K.Acl[4 * i + j] = Aat(4 * (NC + 1) + i, 4 * NC + j);
+      K.Q[4 * i + j] = Pat(i, j);
+      K.QN[4 * i + j] = Pat(4 * NX + i, 4 * NX + j);
+    }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 2; ++j) K.Bd[2 * i + j] = Aat(4 + i, nX + j);
+  for (int i = 0; i < 5; ++i) {
+    for (int j = 0; j < 4; ++j) K.C[4 * i + j] = Aat(nX + i, j);
+    K.Vecr[i] = Aat(nX + i, nX + 2 + i);
+    K.Rs[i] = Pat(nX + 2 + i, nX + 2 + i);
+  }
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) K.Ru[2 * i + j] = Pat(nX + i, nX + j);
+  for (int j = 0; j < 4; ++j) {
+    K.qx[j] = p.c * hp.q_u[j];
+    K.qN[j] = p.c * hp.q_u[4 * NX + j];
+  }
+  K.ulim[0] = hp.u_u[RB];
+  K.ulim[1] = hp.u_u[RB + 1];
+  K.r_p = hp.l_u[nX + 2];
+  // ---- rebuild A, P, q, l, u from the coefficients and compare
+  {
+    std::vector<double> A2((size_t)m * n, 0.0), P2((size_t)n * n, 0.0), q2(n, 0.0);
+    for (int r = 0; r < nX; ++r) A2[(size_t)r * n + r] = -1.0;
+    for (int k = 1; k <= NX; ++k)
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) A2[(size_t)(4 * k + i) * n + 4 * (k - 1) + j] += (k <= NC) ? K.Ad[4 * i + j] : K.Acl[4 * i + j];
+        if (k <= NC)
+          for (int j = 0; j < 2; ++j) A2[(size_t)(4 * k + i) * n + nX + 7 * (k - 1) + j] = K.Bd[2 * i + j];
+        if (i < 2) A2[(size_t)(4 * k + i) * n + n - 2 + i] = 1.0;
+      }
+    for (int k = 0; k <= NX; ++k)
+      for (int i = 0; i < 5; ++i) {
+        for (int j = 0; j < 4; ++j) A2[(size_t)(nX + 5 * k + i) * n + 4 * k + j] = (i < 3) ? K.C[4 * i + j] : (i == 3 ? (j >= 2 ? 1.0 : 0.0) : (j == 1 ? 1.0 : 0.0));
+        if (k < NC) A2[(size_t)(nX + 5 * k + i) * n + nX + 7 * k + 2 + i] = K.Vecr[i];
+      }
+    for (int q = 0; q < 7 * NC; ++q) A2[(size_t)(RB + q) * n + nX + q] = 1.0;
+    A2[(size_t)(m - 2) * n + n - 2] = A2[(size_t)(m - 1) * n + n - 1] = 1.0;
+    for (int k = 0; k <= NX; ++k)
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) P2[(size_t)(4 * k + i) * n + 4 * k + j] = (k < NX) ? K.Q[4 * i + j] : K.QN[4 * i + j];
+        q2[4 * k + i] = ((k < NX) ? K.qx[i] : K.qN[i]);
+      }
+    for (int k = 0; k < NC; ++k) {
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) P2[(size_t)(nX + 7 * k + i) * n + nX + 7 * k + j] = K.Ru[2 * i + j];
+      for (int i = 0; i < 5; ++i) P2[(size_t)(nX + 7 * k + 2 + i) * n + nX + 7 * k + 2 + i] = K.Rs[i];
+    }
+    P2[(size_t)(n - 2) * n + n - 2] = P2[(size_t)(n - 1) * n + n - 1] = 1.0;
+    for (size_t q = 0; q < A2.size(); ++q)
+      if (A2[q] != A[q]) return MPCB_OK;
+    for (size_t q = 0; q < P2.size(); ++q)
+      if (P2[q] != P[q]) return MPCB_OK;
+    for (int j = 0; j < n; ++j)
+      if (q2[j] != p.c * hp.q_u[j]) return MPCB_OK;
+    // bounds the kernel hard-codes
+    for (int k = 0; k <= NX; ++k)
+      for (int i = 0; i < 5; ++i) {
+        const double lo = hp.l_u[nX + 5 * k + i], hi = hp.u_u[nX + 5 * k + i];
+        const double elo = (k <= NB) ? (i < 2 ? 1.0 : (i == 2 ? K.r_p : (i == 3 ? 0.0 : -INFINITY))) : -INFINITY;
+        if (lo != elo) return MPCB_OK;
+        if (!(k <= NB && i == 3) && hi != INFINITY) return MPCB_OK;
+      }
+    for (int k = 0; k < NC; ++k)
+      for (int i = 0; i < 7; ++i) {
+        const double lo = hp.l_u[RB + 7 * k + i], hi = hp.u_u[RB + 7 * k + i];
+        if (i < 2 ? (lo != -K.ulim[i] || hi != K.ulim[i]) : (lo != 0.0 || hi != INFINITY)) return MPCB_OK;
+      }
+    for (int r = 4; r < nX; ++r)
+      if (hp.l_u[r] != 0.0 || hp.u_u[r] != 0.0) return MPCB_OK;
+  }
+  K.c = p.c; K.cinv = 1.0 / p.c; K.sigma = p.sigma; K.alpha = p.alpha; K.eps_abs = p.eps_abs; K.eps_rel = p.eps_rel;
+  K.eps_pinf = p.eps_prim_inf; K.adapt_tol = p.adaptive_rho_tolerance; K.qn_unscaled = h->qn_unscaled; K.qn_scaled = h->qn_scaled;
+  K.check_every = p.check_termination; K.adaptive = p.adaptive_rho; K.adapt_interval = std::max(1, p.adaptive_rho_interval);
+  K.max_iter = p.max_iter;
+  // ---- ownership maps: (slot, quad member) -> natural variable / row index, variable -> GEMM position
+  auto var_of = [&](int slot, int c) -> int {
+    if (slot < 12) { const int r = slot / 4, j = slot % 4, k = 4 * r + c; return k <= NX ? 4 * k + j : -1; }
+    if (slot < 16) { const int r = (slot - 12) / 2, j = (slot - 12) % 2, k = 4 * r + c; return (k >= 1 && k <= NC) ? nX + 7 * (k - 1) + j : -1; }
+    if (slot < 26) { const int r = (slot - 16) / 5, j = (slot - 16) % 5, k = 4 * r + c; return k < NC ? nX + 7 * k + 2 + j : -1; }
+    return n - 2 + (slot - 26);
+  };
+  auto row_of = [&](int slot, int c) -> int {
+    if (slot < 12) { const int r = slot / 4, i = slot % 4, k = 4 * r + c; return k <= NX ? 4 * k + i : -1; }
+    if (slot < 27) { const int r = (slot - 12) / 5, i = (slot - 12) % 5, k = 4 * r + c; return k <= NX ? nX + 5 * k + i : -1; }
+    if (slot < 31) { const int r = (slot - 27) / 2, i = (slot - 27) % 2, k = 4 * r + c; return (k >= 1 && k <= NC) ? RB + 7 * (k - 1) + i : -1; }
+    if (slot < 41) { const int r = (slot - 31) / 5, i = (slot - 31) % 5, k = 4 * r + c; return k < NC ? RB + 7 * k + 2 + i : -1; }
+    return m - 2 + (slot - 41);
+  };
+  std::vector<int> pos_of(n, -1);
+  for (int c = 0; c < 4; ++c) {
+    for (int r = 0; r < 3; ++r)
+      for (int j = 0; j < 4; ++j) { const int v = var_of(WVS_X(r, j), c); if (v >= 0) pos_of[v] = 16 * r + 4 * j + c; }
+    for (int r = 0; r < 2; ++r) {
+      for (int j = 0; j < 2; ++j) { const int v = var_of(WVS_U(r, j), c); if (v >= 0) pos_of[v] = (r == 0) ? 48 + 3 * j + (c - 1) : 54 + 2 * j + c; }
+      for (int j = 0; j < 5; ++j) { const int v = var_of(WVS_S(r, j), c); if (v >= 0) pos_of[v] = (r == 0) ? 58 + 4 * j + c : 78 + j; }
+    }
+  }
+  pos_of[n - 2] = 35;
+  pos_of[n - 1] = 39;
+  {
+    std::vector<int> seen(WAVE_LD, 0);
+    for (int v = 0; v < n; ++v) {
+      if (pos_of[v] < 0 || pos_of[v] >= WAVE_LD || seen[pos_of[v]]++) return fail(MPCB_ERR_INVALID, "wave kernel: GEMM position map is not a bijection");
+    }
+  }
+  int off = 0;
+  auto take = [&](size_t bytes) {
+    const int o = off;
+    off = align16(off + (int)bytes);
+    return o;
+  };
+  WaveHdr hd;
+  memset(&hd, 0, sizeof hd);
+  hd.off_Vp = take((size_t)8 * 88 * WAVE_LD);
+  hd.off_lam = take(8 * 88);
+  hd.off_sgD = take(8 * WAVE_NVS * 4); hd.off_Dv = take(8 * WAVE_NVS * 4); hd.off_Dinv = take(8 * WAVE_NVS * 4);
+  hd.off_e2 = take(16 * WAVE_NRS * 4);
+  hd.off_Ev = take(8 * WAVE_NRS * 4); hd.off_Einv = take(8 * WAVE_NRS * 4);
+  hd.off_M1 = take(8 * 32);
+  hd.total = off;
+  h->wave_smem = (size_t)hd.total + (size_t)WAVE_WARPS * 8 * (WAVE_LD + WAVE_LDV + WAVE_LD) * 8;
+  if (h->wave_smem > 227 * 1024) return MPCB_OK;
+  for (int v = 0; v < 4; ++v) {
+    std::vector<unsigned char> b(hd.total, 0);
+    auto dv = [&](int o) { return reinterpret_cast<double *>(b.data() + o); };
+    const double *V = hp.V.data() + (size_t)v * n * n;
+    for (int var = 0; var < n; ++var)
+      for (int J = 0; J < n; ++J) dv(hd.off_Vp)[(size_t)pos_of[var] * WAVE_LD + J] = hp.D[var] * V[(size_t)var * n + J];
+    for (int J = 0; J < n; ++J) dv(hd.off_lam)[J] = hp.lam[(size_t)v * n + J];
+    for (int slot = 0; slot < WAVE_NVS; ++slot)
+      for (int c = 0; c < 4; ++c) {
+        const int var = var_of(slot, c);
+        const double D = var >= 0 ? hp.D[var] : 1.0;
+        dv(hd.off_sgD)[4 * slot + c] = var >= 0 ? p.sigma / (D * D) : 0.0;
+        dv(hd.off_Dv)[4 * slot + c] = D;
+        dv(hd.off_Dinv)[4 * slot + c] = 1.0 / D;
+      }
+    for (int slot = 0; slot < WAVE_NRS; ++slot)
+      for (int c = 0; c < 4; ++c) {
+        const int row = row_of(slot, c);
+        const double E = row >= 0 ? hp.E[row] : 1.0;
+        double e2 = 1.0;
+        if (row >= 0) e2 = hp.ctype[row] == -1 ? -(MPCB_RHO_MIN * E * E) : (hp.ctype[row] == 1 ? MPCB_RHO_EQ * E * E : E * E);
+        dv(hd.off_e2)[2 * (4 * slot + c)] = e2;
+        dv(hd.off_e2)[2 * (4 * slot + c) + 1] = 1.0 / fabs(e2);
+        dv(hd.off_Ev)[4 * slot + c] = E;
+        dv(hd.off_Einv)[4 * slot + c] = 1.0 / E;
+      }
+    for (int q = 0; q < 16; ++q) {
+      dv(hd.off_M1)[q] = K.Ad[q];
+      dv(hd.off_M1)[16 + q] = K.Acl[q];
+    }
+    CK(cudaMalloc(&h->d_wave_blob[v], hd.total));
+    CK(cudaMemcpy(h->d_wave_blob[v], b.data(), hd.total, cudaMemcpyHostToDevice));
+  }
+  CK(cudaFuncSetAttribute((const void *)admm_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wave_smem));
+  h->wave_hdr = hd;
+  h->wave_k = K;
+  h->wave_ok = true;
+  if (const char *e = getenv("MPCB_WAVE_MIN_LANES")) h->wave_min_lanes = atoll(e);
+  return MPCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-lane path tables: sparsity pattern of A (CSR + CSC view) with entry kinds, P in COO, unscaled vectors.
 template <typename Tv>
@@ -855,6 +1047,13 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
     hp.V.assign(pr->V, pr->V + (size_t)4 * n * n);
     hp.lam.assign(pr->lam, pr->lam + (size_t)4 * n);
     hp.ctype.assign(pr->ctype, pr->ctype + m);
+    if (pr->P_u && pr->q_u && pr->A_u && pr->l_u && pr->u_u) {     // unscaled data: the wave kernel iterates in unscaled variables
+      hp.P_u.assign(pr->P_u, pr->P_u + (size_t)n * n);
+      hp.q_u.assign(pr->q_u, pr->q_u + n);
+      hp.A_u.assign(pr->A_u, pr->A_u + (size_t)m * n);
+      hp.l_u.assign(pr->l_u, pr->l_u + m);
+      hp.u_u.assign(pr->u_u, pr->u_u + m);
+    }
   }
   hp.p.P_s = hp.p.q_s = hp.p.A_s = hp.p.l_s = hp.p.u_s = hp.p.D = hp.p.E = hp.p.V = hp.p.lam = nullptr;
   hp.p.ctype = nullptr;
@@ -885,6 +1084,7 @@ extern "C" int mpcb_create(const mpcb_problem *pr, int device, mpcb_handle **out
       set_warps(h, h->warps);
       rc = build_team_tables(h);
       if (rc == MPCB_OK) rc = build_tile_tables(h);
+      if (rc == MPCB_OK) rc = build_wave_tables(h);
     }
   }
   if (rc != MPCB_OK) {
@@ -927,6 +1127,7 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
   cudaFree(h->d_tot);
   cudaFree(h->gen_scratch);
   for (int v = 0; v < 4; ++v) cudaFree(h->d_tile_blob[v]);
+  for (int v = 0; v < 4; ++v) cudaFree(h->d_wave_blob[v]);
   for (void *q : h->gen_bufs) cudaFree(q);
   for (StageBuf &b : h->stage_pool) cudaFree(b.ptr);
   cudaFree(h->d_tblob);
@@ -1023,6 +1224,11 @@ extern "C" int mpcb_get_counters(mpcb_handle *h, mpcb_counters *out) {
 
 extern "C" void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
 
+extern "C" int mpcb_solver_blocks(mpcb_handle *h) {
+  if (!h) return 0;
+  return (h->kern.fn ? 1 : 0) | (h->team_ok ? 2 : 0) | (h->tile_ok ? 4 : 0) | (h->wave_ok ? 8 : 0) | (h->generic_ok ? 16 : 0);
+}
+
 extern "C" int mpcb_wait_stream(mpcb_handle *h, void *producer_stream) {
   if (!h) return fail(MPCB_ERR_INVALID, "null handle");
   CK(cudaSetDevice(h->device));
@@ -1070,6 +1276,12 @@ static bool want_tile(const mpcb_handle *h) {
   if (e && *e) return strcmp(e, "tile") == 0;
   return h->B >= h->tile_min_lanes;
 }
+static bool want_wave(const mpcb_handle *h, bool round_based) {
+  if (!h->wave_ok) return false;
+  const char *e = getenv("MPCB_SOLVER");
+  if (e && *e) return strcmp(e, "wave") == 0;
+  return round_based && h->B >= h->wave_min_lanes;      // whole-loop discrete runs stay on the team kernel (see simulate())
+}
 static bool want_team(const mpcb_handle *h) {
   if (!h->team_ok) return false;
   const char *e = getenv("MPCB_SOLVER");
@@ -1077,11 +1289,11 @@ static bool want_team(const mpcb_handle *h) {
   return true;
 }
 
-static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false) {
+static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false, bool use_wave = false) {
   const int64_t B = h->B;
   // n = 81 family: each round solves its lanes to completion on the team kernel (list mode) instead of advancing them
   // check_termination iterations at a time; rounds then coincide with control steps
-  const bool use_team = !use_tile && want_team(h);
+  const bool use_team = !use_tile && !use_wave && want_team(h);
   if (const char *e = getenv("MPCB_VISIT_ITERS")) h->visit_iters = std::max(-1, atoi(e));
   if (use_team && h->team_tm && !h->scache_tried) {
     h->scache_tried = true;
@@ -1145,6 +1357,19 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
       const int tgrid = (int)std::min<long>(live, (long)h->num_sms * h->team_ctas);
       ((team_fn)h->team_fn_ptr)<<<tgrid, h->team_threads, h->team_smem, h->stream>>>(ta);
+    } else if (use_wave) {
+      WaveArgs wa;
+      memset(&wa, 0, sizeof wa);
+      wa.hdr = h->wave_hdr;
+      wa.k = h->wave_k;
+      for (int v = 0; v < 4; ++v) wa.blob[v] = h->d_wave_blob[v];
+      wa.B = aa.B;
+      wa.cnt = aa.cnt; wa.list = aa.list; wa.xs = aa.xs; wa.zs = aa.zs; wa.ys = aa.ys; wa.rho = aa.rho; wa.iter = aa.iter;
+      wa.status = aa.status; wa.par = aa.par; wa.u0 = aa.u0; wa.lane_state = aa.lane_state; wa.flip = aa.flip;
+      wa.iter_total = aa.iter_total;
+      int wgrid = 0;
+      for (int v = 0; v < 4; ++v) wgrid += (h->h_cnt[v] + 8 * WAVE_WARPS - 1) / (8 * WAVE_WARPS);
+      admm_wave_kernel<<<wgrid, 32 * WAVE_WARPS, h->wave_smem, h->stream>>>(wa);
     } else if (use_tile) {
       TileArgs ta;
       memset(&ta, 0, sizeof ta);
@@ -1292,7 +1517,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
     pa.list_next = h->list;
     qp_prepare_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_xhat);
     h->ctr.kernel_launches += 1;
-    RC(run_rounds(h, aa, pa, 0, want_tile(h)));
+    RC(run_rounds(h, aa, pa, 0, want_tile(h), !want_tile(h) && want_wave(h, true)));
   }
   if (d_u0) CK(cudaMemcpyAsync(d_u0, h->u0, (size_t)2 * B * 8, cudaMemcpyDeviceToDevice, h->stream));
   if (d_st || d_it) {
@@ -1488,7 +1713,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;
-    RC(run_rounds(h, aa, pa, 0, want_tile(h)));
+    RC(run_rounds(h, aa, pa, 0, want_tile(h), !want_tile(h) && want_wave(h, true)));
     finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;

@@ -128,6 +128,8 @@ class Engine:
         else:
             table("P_s", p.P_s); table("q_s", p.q_s); table("A_s", p.A_s); table("l_s", p.l_s); table("u_s", p.u_s)
             table("D", p.D); table("E", p.E); table("ctype", p.ctype, np.int32); table("V", p.V); table("lam", p.lam)
+            # unscaled data as well: the multi-RHS (wave) solver block iterates in unscaled variables
+            table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
         cp.K_dead[:] = np.asarray(p.K_dead, float).reshape(-1).tolist()
         cp.Ki_dead[:] = np.asarray(p.Ki_dead, float).reshape(-1).tolist()
         cp.c = p.c
@@ -163,6 +165,11 @@ class Engine:
         c = _lib.MpcbCounters()
         _lib.check(self.lib.mpcb_get_counters(self._h, C.byref(c)))
         return {k: getattr(c, k) for k, _ in c._fields_}
+
+    def solver_blocks(self) -> dict:
+        """Which solver blocks this problem family can run on (``mpcb_solver_blocks``)."""
+        m = int(self.lib.mpcb_solver_blocks(self._h))
+        return {"block": bool(m & 1), "team": bool(m & 2), "tile": bool(m & 4), "wave": bool(m & 8), "generic": bool(m & 16)}
 
     @property
     def stream(self) -> int:
