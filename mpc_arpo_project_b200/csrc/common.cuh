@@ -79,7 +79,8 @@ struct SimOutDev {
   int T1, NS;
 };
 
-enum : int { MODE_QP_ONLY = 0, MODE_DISCRETE = 1, MODE_CONTINUOUS = 2 };
+enum : int { MODE_QP_ONLY = 0, MODE_DISCRETE = 1, MODE_CONTINUOUS = 2,
+             MODE_RESUME = 3 };     // team kernel only: take over the listed lanes of a round-based discrete simulation mid-flight
 
 struct PostArgs {
   SimConst sc;

@@ -822,10 +822,10 @@ static int build_wave_tables(mpcb_handle *h) {
   };
   WaveHdr hd;
   memset(&hd, 0, sizeof hd);
-  hd.off_Vp = take((size_t)8 * 88 * WAVE_LD);
+  hd.off_Vp = take((size_t)8 * (88 * WAVE_LD + 8));
   hd.off_lam = take(8 * 88);
   hd.off_sgD = take(8 * WAVE_NVS * 4); hd.off_Dv = take(8 * WAVE_NVS * 4); hd.off_Dinv = take(8 * WAVE_NVS * 4);
-  hd.off_e2 = take(16 * WAVE_NRS * 4);
+  hd.off_ka = take(8 * WAVE_NRS * 4); hd.off_kb = take(8 * WAVE_NRS * 4); hd.off_kie = take(8 * WAVE_NRS * 4);
   hd.off_Ev = take(8 * WAVE_NRS * 4); hd.off_Einv = take(8 * WAVE_NRS * 4);
   hd.off_M1 = take(8 * 32);
   hd.total = off;
@@ -850,10 +850,15 @@ static int build_wave_tables(mpcb_handle *h) {
       for (int c = 0; c < 4; ++c) {
         const int row = row_of(slot, c);
         const double E = row >= 0 ? hp.E[row] : 1.0;
-        double e2 = 1.0;
-        if (row >= 0) e2 = hp.ctype[row] == -1 ? -(MPCB_RHO_MIN * E * E) : (hp.ctype[row] == 1 ? MPCB_RHO_EQ * E * E : E * E);
-        dv(hd.off_e2)[2 * (4 * slot + c)] = e2;
-        dv(hd.off_e2)[2 * (4 * slot + c) + 1] = 1.0 / fabs(e2);
+        // kap_i = ka * rho + kb: free rows carry the constant rho_min E^2, the others the class factor (1e3 on equalities) x E^2
+        double ka = 1.0, kb = 0.0;
+        if (row >= 0) {
+          if (hp.ctype[row] == -1) { ka = 0.0; kb = MPCB_RHO_MIN * E * E; }
+          else ka = (hp.ctype[row] == 1 ? MPCB_RHO_EQ : 1.0) * E * E;
+        }
+        dv(hd.off_ka)[4 * slot + c] = ka;
+        dv(hd.off_kb)[4 * slot + c] = kb;
+        dv(hd.off_kie)[4 * slot + c] = ka != 0.0 ? 1.0 / ka : 1.0;       // free rows keep y = 0: their 1 / kap is never used
         dv(hd.off_Ev)[4 * slot + c] = E;
         dv(hd.off_Einv)[4 * slot + c] = 1.0 / E;
       }
@@ -1289,7 +1294,8 @@ static bool want_team(const mpcb_handle *h) {
   return true;
 }
 
-static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false, bool use_wave = false) {
+static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf, bool use_tile = false, bool use_wave = false,
+                      const TeamArgs *resume = nullptr, long resume_below = 0) {
   const int64_t B = h->B;
   // n = 81 family: each round solves its lanes to completion on the team kernel (list mode) instead of advancing them
   // check_termination iterations at a time; rounds then coincide with control steps
@@ -1326,6 +1332,20 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       live += h->h_cnt[v];
     }
     if (live == 0) break;
+    if (resume && live <= resume_below) {
+      // few lanes left: a round would leave most SMs idle and still cost a full launch + 25-iteration latency.  The team kernel
+      // takes the listed lanes over mid-flight (MODE_RESUME) and carries each to the end of its trajectory in ONE launch.
+      TeamArgs ta = *resume;
+      ta.cnt = h->cnt + 4 * cur;
+      ta.list = h->list + (size_t)4 * B * cur;
+      CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+      const int tgrid = (int)std::min<long>(live, (long)h->num_sms * h->team_ctas);
+      ((team_fn)h->team_fn_ptr)<<<tgrid, h->team_threads, h->team_smem, h->stream>>>(ta);
+      CK(cudaGetLastError());
+      h->ctr.kernel_launches += 1;
+      h->ctr.rounds += 1;
+      break;
+    }
     aa.cnt = h->cnt + 4 * cur;
     aa.list = h->list + (size_t)4 * B * cur;
     pa.cnt_cur = h->cnt + 4 * cur;
@@ -1713,7 +1733,23 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;
-    RC(run_rounds(h, aa, pa, 0, want_tile(h), !want_tile(h) && want_wave(h, true)));
+    TeamArgs tr;
+    const bool can_resume = mode == MODE_DISCRETE && h->team_ok && !getenv("MPCB_NO_RESUME");
+    if (can_resume) {
+      fill_team_args(h, tr, MODE_RESUME);
+      tr.nsteps = nsteps;
+      tr.out = od;
+      tr.noise_in = d_noise;
+      tr.n_refresh = n_refresh;
+      tr.warm = 1;
+      tr.ls = h->ls;
+      tr.par = h->par;
+      tr.lane_state = h->lane_state;
+      tr.visit_iters = 0;
+    }
+    long below = 10L * h->num_sms * h->team_ctas;
+    if (const char *e = getenv("MPCB_RESUME_BELOW")) below = atol(e);
+    RC(run_rounds(h, aa, pa, 0, want_tile(h), !want_tile(h) && want_wave(h, true), can_resume ? &tr : nullptr, below));
     finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;

@@ -92,8 +92,10 @@ struct TeamArgs {
   int n, m, nX, Nb, uoff, B;
   double sigma, alpha, eps_abs, eps_rel, eps_pinf, adapt_tol, cinv, qn_unscaled, qn_scaled, rho0;
   int check_every, adaptive, adapt_interval, max_iter;
-  int mode;                  // MODE_QP_ONLY | MODE_DISCRETE
+  int mode;                  // MODE_QP_ONLY | MODE_DISCRETE | MODE_RESUME
   int nsteps;
+  LaneSim ls;                // MODE_RESUME: the round-based simulators' per-lane state (sim.cuh), read at lane start and written back at
+                             // the lane's end; the listed lanes (cnt / list) are carried to the end of their trajectories
   SimConst sc;
   SimOutDev out;
   const double *x0;          // [4][B]
@@ -132,7 +134,7 @@ struct TeamArgs {
 struct LaneCtx {
   double xtrue[4], ux[6], uP[36], xstore[4], unext[2], noise[2], xfin[4], par[7], u0[2];
   double xintf, rho;
-  int step, iterm, succ, nsolve, variant, ukf_clamp, flip, fin, status, iter, lane;
+  int step, iterm, succ, nsolve, nsolve0, variant, ukf_clamp, flip, fin, status, iter, lane;
   double c_rho;              // operator-cache tag of this lane
   int c_var;
 };
@@ -404,6 +406,31 @@ __device__ __noinline__ void lane_init(const TeamArgs &a, LaneCtx &L, int ln) {
   L.u0[0] = L.u0[1] = 0.0;
   L.c_rho = -1.0;
   L.c_var = -1;
+  L.nsolve0 = 0;
+  if (a.mode == MODE_RESUME) {           // mid-flight lane of a round-based run (variant came with the list it was drawn from)
+    for (int k = 0; k < 7; ++k) L.par[k] = a.par[k * B + ln];
+    for (int k = 0; k < 4; ++k) {
+      L.xtrue[k] = a.ls.xtrue[k * B + ln];
+      L.xstore[k] = a.ls.xstore[k * B + ln];
+      L.xfin[k] = a.ls.xfin[k * B + ln];
+    }
+    for (int k = 0; k < 6; ++k) L.ux[k] = a.ls.ux[k * B + ln];
+    for (int k = 0; k < 36; ++k) L.uP[k] = a.ls.uP[k * B + ln];
+    for (int k = 0; k < 2; ++k) {
+      L.unext[k] = a.ls.unext[k * B + ln];
+      L.noise[k] = a.ls.noise[k * B + ln];
+    }
+    L.xintf = a.ls.xintf[ln];
+    L.rho = a.rho[ln];
+    L.iter = a.iter[ln];                 // iterations the lane's current solve has already done
+    L.step = a.ls.step[ln];
+    L.iterm = a.ls.iterm[ln];
+    L.succ = a.ls.succ[ln];
+    L.nsolve = L.nsolve0 = a.ls.nsolve[ln];
+    L.ukf_clamp = a.ls.ukf_clamp[ln];
+    L.flip = a.flip[ln];
+    return;
+  }
   if (a.mode == MODE_QP_ONLY) {
     if (a.list) {            // variant was set by the caller (it comes with the list the lane was drawn from)
       for (int k = 0; k < 7; ++k) L.par[k] = a.par[k * B + ln];
@@ -444,6 +471,23 @@ __device__ __noinline__ void lane_init(const TeamArgs &a, LaneCtx &L, int ln) {
 
 __device__ __noinline__ void lane_finalize(const TeamArgs &a, LaneCtx &L) {
   const int ln = L.lane;
+  if (a.mode == MODE_RESUME) {           // hand the finished lane back: finalize_kernel reduces every lane from LaneSim
+    const size_t B = a.B;
+    for (int k = 0; k < 4; ++k) {
+      a.ls.xfin[k * B + ln] = L.xfin[k];
+      a.ls.xtrue[k * B + ln] = L.xtrue[k];
+    }
+    a.ls.iterm[ln] = L.iterm;
+    a.ls.succ[ln] = L.succ;
+    a.ls.nsolve[ln] = L.nsolve;
+    a.ls.step[ln] = L.step;
+    a.ls.ukf_clamp[ln] = L.ukf_clamp;
+    a.rho[ln] = L.rho;
+    if (L.flip) a.flip[ln] = 1;
+    a.lane_state[ln] = LANE_FINISHED;
+    atomicAdd(&a.tot[1], (unsigned long long)(L.nsolve - L.nsolve0));
+    return;
+  }
   if (a.mode == MODE_QP_ONLY) {
     a.status[ln] = L.status;
     a.iter[ln] = L.iter;
@@ -840,6 +884,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
     const int ln = s_lane;
     if (ln >= a.B) break;
     if (tid == 0) lane_init(a, L, ln);
+    bool first_solve = true;             // list / resume modes: the lane's first solve here may already be under way
     // solver iterates: x[col] (both pair members), z[row] / y[row]
     double x = 0.0, z = 0.0, y = 0.0;
     if (a.warm) {
@@ -884,7 +929,8 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
           }
         }
       }
-      int iter = a.list ? L.iter : 0, st = -10;        // list mode: a solve may span several visits
+      int iter = (a.list && first_solve) ? L.iter : 0, st = -10;        // list mode: a solve may span several visits
+      first_solve = false;
       int visit_left = a.visit_iters;
       const bool resigned = variant != op_variant;
       bool need_op = (variant != s_variant) || (rho != op_rho);

@@ -48,7 +48,7 @@ struct WaveHdr {          // byte offsets into the per-variant blob (global -> s
   int off_Vp;             // [88][WAVE_LD] doubles: Vp[p][J] = D[var(p)] V[var(p)][J], zero rows at unused positions
   int off_lam;            // [88]
   int off_sgD, off_Dv, off_Dinv;          // [NVS][4]: sigma / D^2, D, 1 / D of the variable (slot, quad member)
-  int off_e2;             // [NRS][4] double2: (kap factor, its reciprocal): rho-class factor x E^2; NEGATIVE = free row (kap = -value)
+  int off_ka, off_kb, off_kie;            // [NRS][4]: kap_i = ka rho + kb (free rows: ka = 0, kb = rho_min E^2; else ka = class factor x E^2, kb = 0); 1 / ka
   int off_Ev, off_Einv;   // [NRS][4]
   int off_M1;             // [2][16]: Ad, Ad - Bd K (slot 1 mixes the two kinds of stage)
   int total;
@@ -150,18 +150,62 @@ __device__ __forceinline__ void wtm_st2(uint32_t a, const double (&v)[2]) {
 #define WRS_BS(r, i) (31 + (r) * 5 + (i))
 #define WRS_PIN(i) (41 + (i))
 
-// One ADMM row update (OSQP update_z / update_y in the unscaled variables); returns v = kap z - y for the next A' product.
+// ---- batched tensor-memory loads: issue, issue, ..., ONE wait that names every destination register (the compiler must
+//      not move a use of them above the wait)
+__device__ __forceinline__ void wtm_ld8_nw(uint32_t a, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
+}
+__device__ __forceinline__ void wtm_ld4_nw(uint32_t a, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+#define WTM_R8(a) "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])
+#define WTM_R4(a) "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3])
+__device__ __forceinline__ void wtm_wait_stage(uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8], uint32_t (&d)[4], uint32_t (&e)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : WTM_R8(a), WTM_R8(b), WTM_R8(c), WTM_R4(d), WTM_R8(e) :: "memory");
+}
+__device__ __forceinline__ void wtm_wait_box(uint32_t (&a)[4], uint32_t (&b)[4], uint32_t (&c)[8], uint32_t (&d)[4], uint32_t (&e)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : WTM_R4(a), WTM_R4(b), WTM_R8(c), WTM_R4(d), WTM_R8(e) :: "memory");
+}
+__device__ __forceinline__ void wtm_wait_dy(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : WTM_R8(a), WTM_R8(b) :: "memory");
+}
+__device__ __forceinline__ void wtm_wait_dybox(uint32_t (&a)[4], uint32_t (&b)[8], uint32_t (&c)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : WTM_R4(a), WTM_R8(b), WTM_R4(c) :: "memory");
+}
+__device__ __forceinline__ double wd(const uint32_t *r, int i) { return u2d(r[2 * i], r[2 * i + 1]); }
+__device__ __forceinline__ void wtm_st8_raw(uint32_t a, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// spectral index of column n of an 8-wide tile: with this order BOTH GEMMs read their B fragments from the one table Vp
+// (row stride 84 = 4 mod 16) without bank conflicts, and the C fragment of GEMM 1 is still the A fragment of GEMM 2
+__device__ __forceinline__ int wave_pi(int n) { return n < 4 ? n : (n ^ 1); }        // {0,1,2,3,5,4,7,6}
+
+// ADMM row updates (OSQP update_z / update_y in the unscaled variables), one flavour per kind of row; each returns
+// v = kap z - y, the row's entry of the next A' product.
 struct WaveRow {
   double alpha, oma, rho, rinv;
-  const double2 *e2;      // + 4 * slot + c
-  __device__ __forceinline__ void kap(int slot, double &k, double &ik) const {
-    const double2 t = e2[4 * slot];
-    k = t.x < 0.0 ? -t.x : rho * t.x;
-    ik = t.x < 0.0 ? t.y : rinv * t.y;
+  const double *ka, *kb, *kie;      // + 4 * slot (+ c folded in)
+  // equality row (l = u = b): the projection is b itself
+  __device__ __forceinline__ double eq(int slot, double zt, double &z, double &y, double b, double &dy) const {
+    const double k = rho * ka[4 * slot];
+    const double zr = alpha * zt + oma * z;
+    dy = k * (zr - b);
+    y += dy;
+    z = b;
+    return k * b - y;
   }
-  __device__ __forceinline__ double upd(int slot, double zt, double &z, double &y, double lo, double hi, double &dy) const {
-    double k, ik;
-    kap(slot, k, ik);
+  // free row (both bounds infinite): kap = rho_min E^2, y stays 0
+  __device__ __forceinline__ double fr(int slot, double zt, double &z) const {
+    z = alpha * zt + oma * z;
+    return kb[4 * slot] * z;
+  }
+  // general row; lo / hi may be -+WAVE_INF.  Free rows pass through here too when the kind is only known per thread
+  // (ka = 0, kb = rho_min E^2, y = 0, infinite bounds).
+  __device__ __forceinline__ double gen(int slot, double zt, double &z, double &y, double lo, double hi, double &dy) const {
+    const double k = fma(ka[4 * slot], rho, kb[4 * slot]), ik = rinv * kie[4 * slot];
     const double zr = alpha * zt + oma * z;
     const double zn = fmin(fmax(zr + ik * y, lo), hi);
     dy = k * (zr - zn);
@@ -169,11 +213,17 @@ struct WaveRow {
     z = zn;
     return k * zn - y;
   }
-  __device__ __forceinline__ double vee(int slot, double z, double y) const {      // v of the current (z, y): first iteration of a round
-    double k, ik;
-    kap(slot, k, ik);
-    return k * z - y;
+  // lower bound only
+  __device__ __forceinline__ double lo1(int slot, double zt, double &z, double &y, double lo, double &dy) const {
+    const double k = rho * ka[4 * slot], ik = rinv * kie[4 * slot];
+    const double zr = alpha * zt + oma * z;
+    const double zn = fmax(zr + ik * y, lo);
+    dy = k * (zr - zn);
+    y += dy;
+    z = zn;
+    return k * zn - y;
   }
+  __device__ __forceinline__ double vee(int slot, double z, double y) const { return fma(ka[4 * slot], rho, kb[4 * slot]) * z - y; }
 };
 
 __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __grid_constant__ WaveArgs a) {
@@ -211,7 +261,9 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
   const double *sgD = reinterpret_cast<const double *>(smem + h.off_sgD) + c;
   const double *Dv = reinterpret_cast<const double *>(smem + h.off_Dv) + c;
   const double *Dinv = reinterpret_cast<const double *>(smem + h.off_Dinv) + c;
-  const double2 *e2t = reinterpret_cast<const double2 *>(smem + h.off_e2) + c;
+  const double *kat = reinterpret_cast<const double *>(smem + h.off_ka) + c;
+  const double *kbt = reinterpret_cast<const double *>(smem + h.off_kb) + c;
+  const double *kiet = reinterpret_cast<const double *>(smem + h.off_kie) + c;
   const double *Ev = reinterpret_cast<const double *>(smem + h.off_Ev) + c;
   const double *Einv = reinterpret_cast<const double *>(smem + h.off_Einv) + c;
   const double *M1tab = reinterpret_cast<const double *>(smem + h.off_M1);
@@ -340,7 +392,7 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
 
   const double alpha = K.alpha, oma = 1.0 - K.alpha;
   WaveRow R;
-  R.alpha = alpha; R.oma = oma; R.rho = rho; R.rinv = 1.0 / rho; R.e2 = e2t;
+  R.alpha = alpha; R.oma = oma; R.rho = rho; R.rinv = 1.0 / rho; R.ka = kat; R.kb = kbt; R.kie = kiet;
 
   // ---- bounds of this step (unscaled): only x^ (dynamics block 0), the velocity 1-norm bound and the disturbance pin move
   auto los_lo = [&](int r, int i) { return st_b[r] ? (i == 0 || i == 1 ? 1.0 : (i == 2 ? K.r_p : (i == 3 ? 0.0 : -WAVE_INF))) : -WAVE_INF; };
@@ -455,10 +507,10 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
       wtm_ld4(tb + WTM_YS(r), ys4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        vd[i] = okf * R.vee(WRS_DYN(r, i), zd[i], yd[i]);
-        vs[i] = okf * R.vee(WRS_LOS(r, i), zs4[i], ys4[i]);
+        vd[i] = R.vee(WRS_DYN(r, i), zd[i], yd[i]);
+        vs[i] = R.vee(WRS_LOS(r, i), zs4[i], ys4[i]);
       }
-      vs[4] = okf * R.vee(WRS_LOS(r, 4), zs5[0], 0.0);
+      vs[4] = R.vee(WRS_LOS(r, 4), zs5[0], 0.0);
       at_stage(r, vd, vs);
       if (r < 2) {
         double zu[2], yu[2], zb[4], yb[4], zyb[2], vu[2], vbs[5];
@@ -469,10 +521,10 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
         wtm_ld4(tb + WTM_YB(r), yb);
         const double uf = st_u[r] ? 1.0 : 0.0, sf = st_s[r] ? 1.0 : 0.0;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) vu[i] = uf * R.vee(WRS_BU(r, i), zu[i], yu[i]);
+        for (int i = 0; i < 2; ++i) vu[i] = R.vee(WRS_BU(r, i), zu[i], yu[i]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) vbs[i] = sf * R.vee(WRS_BS(r, i), zb[i], yb[i]);
-        vbs[4] = sf * R.vee(WRS_BS(r, 4), zyb[0], zyb[1]);
+        for (int i = 0; i < 4; ++i) vbs[i] = R.vee(WRS_BS(r, i), zb[i], yb[i]);
+        vbs[4] = R.vee(WRS_BS(r, 4), zyb[0], zyb[1]);
         at_box(r, vd, vs, vu, vbs);
       }
     }
@@ -484,6 +536,7 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
   }
 
   // =============================== check_every ADMM iterations ===============================
+  const int pi0 = wave_pi(2 * c), pi1 = wave_pi(2 * c + 1);          // spectral offsets of this thread's two C-fragment columns
   for (int it = 0; tile_live && it < K.check_every; ++it) {
     const bool last = it == K.check_every - 1;
     // ---- x~ = Vp diag(d) Vp' r on the tensor cores
@@ -495,22 +548,31 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
       double acc[2 * NT];
 #pragma unroll
       for (int j = 0; j < 2 * NT; ++j) acc[j] = 0.0;
-      const double *vb1 = Vp + c * LD + 4 * (g & 1) + (g >> 1);      // B[k = 4s + c][J = 8t + 4(g&1) + (g>>1)]
+      const double *vb1 = Vp + c * LD + wave_pi(g);                  // B[k = 4s + c][J = 8t + pi(g)]
 #pragma unroll
       for (int s = 0; s < KS; ++s)
 #pragma unroll
         for (int t = 0; t < NT; ++t) wave_dmma(acc[2 * t], acc[2 * t + 1], af[s], vb1[4 * s * LD + 8 * t]);
-      // thread (g, c) holds T[lane g][J = 8t + 4e + c] in acc[2t + e]; J >= 84 (the padding half of the last tile) is never used
+      // thread (g, c) holds T[lane g][J = 8t + pi(2c + e)] in acc[2t + e]; J >= 84 (last tile, c >= 2) is padding: weight 0
 #pragma unroll
-      for (int j = 0; j < 2 * NT - 1; ++j) acc[j] *= dscb[8 * (j >> 1) + 4 * (j & 1) + c];
-      const double *vb2 = Vp + g * LD + c;                           // B[J = 4ks + c][p = 8t' + g] = Vp[8t' + g][4ks + c]
+      for (int t = 0; t < NT; ++t) {
+        const bool pad = (t == NT - 1) && c >= 2;
+        acc[2 * t] *= pad ? 0.0 : dscb[8 * t + pi0];
+        acc[2 * t + 1] *= pad ? 0.0 : dscb[8 * t + pi1];
+      }
+      // k-step (2t + e) of GEMM 2 covers J = 8t + pi(2c' + e), c' = 0..3: B[J][p = 8t' + g] = Vp[8t' + g][8t + pi(2c + e)]
+      const double *vb2 = Vp + g * LD;
 #pragma unroll
       for (int tp = 0; tp < NT; ++tp) {
-        double x0 = 0.0, x1 = 0.0;
+        // two accumulator pairs per output tile: a lone warp is otherwise bound by the latency of a 22-long DMMA chain
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) wave_dmma(x0, x1, acc[ks], vb2[8 * tp * LD + 4 * ks]);
+        for (int t = 0; t < NT; ++t) {
+          wave_dmma(x0, x1, acc[2 * t], vb2[8 * tp * LD + 8 * t + pi0]);
+          wave_dmma(y0, y1, acc[2 * t + 1], vb2[8 * tp * LD + 8 * t + pi1]);
+        }
         const int p = 8 * tp + 2 * c;
-        if (p < LD) *reinterpret_cast<double2 *>(nb + p) = make_double2(x0, x1);
+        if (p < LD) *reinterpret_cast<double2 *>(nb + p) = make_double2(x0 + y0, x1 + y1);
       }
       __syncwarp();
     }
@@ -520,52 +582,59 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
     dt[1] = nb[pd(1)];
     dd[0] = alpha * dt[0] + oma * dd[0];
     dd[1] = alpha * dt[1] + oma * dd[1];
-    double xt[3][4], ut[2][2], stl[2][5];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        xt[r][j] = st_ok[r] ? nb[px(r, j)] : 0.0;
-        xk[r][j] = alpha * xt[r][j] + oma * xk[r][j];
-      }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ut[r][j] = st_u[r] ? nb[pu(r, j)] : 0.0;
-        uk[r][j] = alpha * ut[r][j] + oma * uk[r][j];
-      }
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        stl[r][j] = st_s[r] ? nb[ps(r, j)] : 0.0;
-        sk[r][j] = alpha * stl[r][j] + oma * sk[r][j];
-      }
-    }
-    r_init();
+    rd[0] = sgD[4 * WVS_D(0)] * dd[0];
+    rd[1] = sgD[4 * WVS_D(1)] * dd[1];
+    dsum[0] = dsum[1] = 0.0;
     double vpin[2];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const double okf = st_ok[r] ? 1.0 : 0.0;
-      // x~ of stage k-1: quad member (c-1) & 3, slot r (r-1 when c = 0)
-      double xm[4];
+      // tensor-memory loads of the slot's rows first: they complete while the products below are computed
+      uint32_t qzd[8], qyd[8], qzs[8], qz5[4], qys[8];
+      wtm_ld8_nw(tb + WTM_ZD(r), qzd);
+      wtm_ld8_nw(tb + WTM_YD(r), qyd);
+      wtm_ld8_nw(tb + WTM_ZS(r), qzs);
+      wtm_ld4_nw(tb + WTM_ZS4(r), qz5);
+      wtm_ld8_nw(tb + WTM_YS(r), qys);
+      // x~ of this stage (own) and of stage k-1 (quad member (c-1) & 3, slot r; slot r-1 when c = 0)
+      double xt[4], xm[4], ut[2] = {0.0, 0.0}, sl[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       {
         const bool okm = ge1[r] != 0.0;
         const int off = (c == 0) ? 16 * (r - 1) + 3 : 16 * r + (c - 1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xm[j] = okm ? (nb)[off + 4 * j] : 0.0;
+        for (int j = 0; j < 4; ++j) {
+          xt[j] = st_ok[r] ? nb[px(r, j)] : 0.0;
+          xm[j] = okm ? nb[off + 4 * j] : 0.0;
+          xk[r][j] = alpha * xt[j] + oma * xk[r][j];
+          const double q = (r == 2 && c == 2) ? K.qN[j] : K.qx[j];
+          rx[r][j] = sgD[4 * WVS_X(r, j)] * xk[r][j] - q;
+        }
+        if (r < 2) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            ut[j] = st_u[r] ? nb[pu(r, j)] : 0.0;
+            uk[r][j] = alpha * ut[j] + oma * uk[r][j];
+            ru[r][j] = sgD[4 * WVS_U(r, j)] * uk[r][j];
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            sl[j] = st_s[r] ? nb[ps(r, j)] : 0.0;
+            sk[r][j] = alpha * sl[j] + oma * sk[r][j];
+            rs[r][j] = sgD[4 * WVS_S(r, j)] * sk[r][j];
+          }
+        }
       }
       double zt_d[4], zt_s[5];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        double acc = -xt[r][i];
+        double acc = -xt[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const double mij = (r == 0) ? K.Ad[4 * i + j] : (r == 2 ? K.Acl[4 * i + j] : M1row[4 * i + j]);
           acc = fma(mij, xm[j], acc);
         }
         if (r < 2) {
-          acc = fma(K.Bd[2 * i], ut[r][0], acc);
-          acc = fma(K.Bd[2 * i + 1], ut[r][1], acc);
+          acc = fma(K.Bd[2 * i], ut[0], acc);
+          acc = fma(K.Bd[2 * i + 1], ut[1], acc);
         }
         if (i < 2) acc = fma(ge1[r], dt[i], acc);
         zt_d[i] = acc;
@@ -574,70 +643,88 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
       for (int i = 0; i < 3; ++i) {
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc = fma(K.C[4 * i + j], xt[r][j], acc);
+        for (int j = 0; j < 4; ++j) acc = fma(K.C[4 * i + j], xt[j], acc);
         zt_s[i] = acc;
       }
-      zt_s[3] = c1 * xt[r][2] + c2 * xt[r][3];
-      zt_s[4] = xt[r][1];
+      zt_s[3] = c1 * xt[2] + c2 * xt[3];
+      zt_s[4] = xt[1];
       if (r < 2) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) zt_s[i] = fma(K.Vecr[i], stl[r][i], zt_s[i]);
+        for (int i = 0; i < 5; ++i) zt_s[i] = fma(K.Vecr[i], sl[i], zt_s[i]);
       }
+      wtm_wait_stage(qzd, qyd, qzs, qz5, qys);
       double zd[4], yd[4], zs4[4], ys4[4], zs5[2], vd[4], vs[5], dyd[4], dys[4];
-      wtm_ld4(tb + WTM_ZD(r), zd);
-      wtm_ld4(tb + WTM_YD(r), yd);
-      wtm_ld4(tb + WTM_ZS(r), zs4);
-      wtm_ld2(tb + WTM_ZS4(r), zs5);
-      wtm_ld4(tb + WTM_YS(r), ys4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        zd[i] = wd(qzd, i); yd[i] = wd(qyd, i); zs4[i] = wd(qzs, i); ys4[i] = wd(qys, i);
+      }
+      zs5[0] = wd(qz5, 0);
+      zs5[1] = 0.0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const double bd = (r == 0 && c == 0) ? -prm[i] : 0.0;              // dynamics block 0: -x^ ; the others: 0
-        vd[i] = okf * R.upd(WRS_DYN(r, i), zt_d[i], zd[i], yd[i], bd, bd, dyd[i]);
-        double dl;
-        vs[i] = okf * R.upd(WRS_LOS(r, i), zt_s[i], zs4[i], ys4[i], los_lo(r, i), los_hi(r, i), dl);
-        dys[i] = (i < 3) ? fmin(dl, 0.0) : dl;                             // rows 0..2 have no upper bound: only dy <= 0 certifies
-        if (!st_b[r]) dys[i] = 0.0;
+        vd[i] = R.eq(WRS_DYN(r, i), zt_d[i], zd[i], yd[i], bd, dyd[i]);
       }
-      {
-        double y4 = 0.0, dl;
-        vs[4] = okf * R.upd(WRS_LOS(r, 4), zt_s[4], zs5[0], y4, -WAVE_INF, WAVE_INF, dl);
+      if (r == 0) {                      // stages 0..3 <= Nb: LOS cone / keep-out rows have a lower bound, the 1-norm row two
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double dl;
+          vs[i] = R.lo1(WRS_LOS(r, i), zt_s[i], zs4[i], ys4[i], i == 2 ? K.r_p : 1.0, dl);
+          dys[i] = fmin(dl, 0.0);        // no upper bound: only dy <= 0 certifies infeasibility
+        }
+        vs[3] = R.gen(WRS_LOS(r, 3), zt_s[3], zs4[3], ys4[3], 0.0, prm[4], dys[3]);
+      } else if (r == 1) {               // stages 4..7: bounded up to Nb, free beyond (per thread)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double dl;
+          vs[i] = R.gen(WRS_LOS(r, i), zt_s[i], zs4[i], ys4[i], los_lo(r, i), los_hi(r, i), dl);
+          dys[i] = st_b[r] ? ((i < 3) ? fmin(dl, 0.0) : dl) : 0.0;
+        }
+      } else {                           // stages 8..: free rows
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vs[i] = R.fr(WRS_LOS(r, i), zt_s[i], zs4[i]);
+          dys[i] = 0.0;
+        }
       }
+      vs[4] = R.fr(WRS_LOS(r, 4), zt_s[4], zs5[0]);                        // half-plane row: free without debris
       wtm_st4(tb + WTM_ZD(r), zd);
       wtm_st4(tb + WTM_YD(r), yd);
       wtm_st4(tb + WTM_ZS(r), zs4);
       wtm_st2(tb + WTM_ZS4(r), zs5);
-      wtm_st4(tb + WTM_YS(r), ys4);
+      if (r < 2) wtm_st4(tb + WTM_YS(r), ys4);
       if (last) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dyd[i] *= okf;
         wtm_st4(tb + WTM_DD(r), dyd);
-        if (r < 2) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dys[i] *= okf;
-          wtm_st4(tb + WTM_DS(r), dys);
-        }
+        if (r < 2) wtm_st4(tb + WTM_DS(r), dys);
       }
       at_stage(r, vd, vs);
       if (r < 2) {
+        uint32_t qzu[4], qyu[4], qzb[8], qzy4[4], qyb[8];
+        wtm_ld4_nw(tb + WTM_ZU(r), qzu);
+        wtm_ld4_nw(tb + WTM_YU(r), qyu);
+        wtm_ld8_nw(tb + WTM_ZB(r), qzb);
+        wtm_ld4_nw(tb + WTM_ZYB4(r), qzy4);
+        wtm_ld8_nw(tb + WTM_YB(r), qyb);
+        wtm_wait_box(qzu, qyu, qzb, qzy4, qyb);
         double zu[2], yu[2], zb[4], yb[4], zyb[2], vu[2], vbs[5], dyu[2], dyb[4], dyb4[2];
-        wtm_ld2(tb + WTM_ZU(r), zu);
-        wtm_ld2(tb + WTM_YU(r), yu);
-        wtm_ld4(tb + WTM_ZB(r), zb);
-        wtm_ld2(tb + WTM_ZYB4(r), zyb);
-        wtm_ld4(tb + WTM_YB(r), yb);
-        const double uf = st_u[r] ? 1.0 : 0.0, sf = st_s[r] ? 1.0 : 0.0;
+        zu[0] = wd(qzu, 0); zu[1] = wd(qzu, 1); yu[0] = wd(qyu, 0); yu[1] = wd(qyu, 1);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) vu[i] = uf * R.upd(WRS_BU(r, i), ut[r][i], zu[i], yu[i], -K.ulim[i], K.ulim[i], dyu[i]);
+        for (int i = 0; i < 4; ++i) {
+          zb[i] = wd(qzb, i); yb[i] = wd(qyb, i);
+        }
+        zyb[0] = wd(qzy4, 0); zyb[1] = wd(qzy4, 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) vu[i] = R.gen(WRS_BU(r, i), ut[i], zu[i], yu[i], -K.ulim[i], K.ulim[i], dyu[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           double dl;
-          vbs[i] = sf * R.upd(WRS_BS(r, i), stl[r][i], zb[i], yb[i], 0.0, WAVE_INF, dl);
-          dyb[i] = sf * fmin(dl, 0.0);
+          vbs[i] = R.lo1(WRS_BS(r, i), sl[i], zb[i], yb[i], 0.0, dl);
+          dyb[i] = fmin(dl, 0.0);
         }
         {
           double dl;
-          vbs[4] = sf * R.upd(WRS_BS(r, 4), stl[r][4], zyb[0], zyb[1], 0.0, WAVE_INF, dl);
-          dyb4[0] = sf * fmin(dl, 0.0);
+          vbs[4] = R.lo1(WRS_BS(r, 4), sl[4], zyb[0], zyb[1], 0.0, dl);
+          dyb4[0] = fmin(dl, 0.0);
           dyb4[1] = 0.0;
         }
         wtm_st2(tb + WTM_ZU(r), zu);
@@ -646,8 +733,6 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
         wtm_st2(tb + WTM_ZYB4(r), zyb);
         wtm_st4(tb + WTM_YB(r), yb);
         if (last) {
-          dyu[0] *= uf;
-          dyu[1] *= uf;
           wtm_st2(tb + WTM_DU(r), dyu);
           wtm_st4(tb + WTM_DB(r), dyb);
           wtm_st2(tb + WTM_DB4(r), dyb4);
@@ -658,8 +743,8 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
     {
       double pin4[4], dyp[2];
       wtm_ld4(tb + WTM_PIN, pin4);
-      vpin[0] = R.upd(WRS_PIN(0), dt[0], pin4[0], pin4[2], prm[5], prm[5], dyp[0]);
-      vpin[1] = R.upd(WRS_PIN(1), dt[1], pin4[1], pin4[3], prm[6], prm[6], dyp[1]);
+      vpin[0] = R.eq(WRS_PIN(0), dt[0], pin4[0], pin4[2], prm[5], dyp[0]);
+      vpin[1] = R.eq(WRS_PIN(1), dt[1], pin4[1], pin4[3], prm[6], dyp[1]);
       wtm_st4(tb + WTM_PIN, pin4);
       if (last) wtm_st2(tb + WTM_DP, dyp);
     }
