@@ -10,4 +10,5 @@ from .problem import Problem, SolverSettings, build_problem  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .trajectorySimulate import trajectorySimulate, trajectorySimulateBatch  # noqa: F401
 from .trajectorySimulateC import trajectorySimulateC, trajectorySimulateCBatch, build_problem_c  # noqa: F401
-from .montecarlo import final_distance_ratio_sweep, success_rate  # noqa: F401
+from .montecarlo import RatioSweep, final_distance_ratio_sweep, success_rate  # noqa: F401
+from . import presets  # noqa: F401

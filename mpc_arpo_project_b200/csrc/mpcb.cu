@@ -1285,7 +1285,10 @@ static bool want_wave(const mpcb_handle *h, bool round_based) {
   if (!h->wave_ok) return false;
   const char *e = getenv("MPCB_SOLVER");
   if (e && *e) return strcmp(e, "wave") == 0;
-  return round_based && h->B >= h->wave_min_lanes;      // whole-loop discrete runs stay on the team kernel (see simulate())
+  // Large batches: rounds of the multi-RHS wave kernel (2x the team kernel's throughput once every SM holds 64 lanes), the
+  // last lanes handed to the team kernel mid-flight.  Small batches stay on the team kernel's whole-loop launch: a round
+  // of 4096 lanes would fill 64 of 148 SMs.
+  return round_based && h->B >= h->wave_min_lanes;
 }
 static bool want_team(const mpcb_handle *h) {
   if (!h->team_ok) return false;
@@ -1340,9 +1343,19 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       ta.list = h->list + (size_t)4 * B * cur;
       CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
       const int tgrid = (int)std::min<long>(live, (long)h->num_sms * h->team_ctas);
+      if (h->timing) {
+        while (h->ev_pool.size() < ev_used + 2) {
+          cudaEvent_t e;
+          CK(cudaEventCreate(&e));
+          h->ev_pool.push_back(e);
+        }
+        CK(cudaEventRecord(h->ev_pool[ev_used++], h->stream));
+      }
       ((team_fn)h->team_fn_ptr)<<<tgrid, h->team_threads, h->team_smem, h->stream>>>(ta);
       CK(cudaGetLastError());
+      if (h->timing) CK(cudaEventRecord(h->ev_pool[ev_used++], h->stream));
       h->ctr.kernel_launches += 1;
+      h->ctr.admm_launches += 1;
       h->ctr.rounds += 1;
       break;
     }
@@ -1417,6 +1430,7 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
     cur = 1 - cur;
   }
   if (h->timing) {
+    CK(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i + 1 < ev_used; i += 2) {
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
@@ -1715,7 +1729,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     g.n_refresh = n_refresh;
     g.warm = 0;
     RC(launch_generic(h, g));
-  } else if (!want_tile(h) && want_team(h) && mode == MODE_DISCRETE) {
+  } else if (!want_tile(h) && !want_wave(h, true) && want_team(h) && mode == MODE_DISCRETE) {
     TeamArgs ta;
     fill_team_args(h, ta, MODE_DISCRETE);
     ta.nsteps = nsteps;

@@ -79,6 +79,55 @@ class _Arrays:
         return a, C.c_void_p(a.ctypes.data)
 
 
+def fill_problem_struct(problem: Problem):
+    """``struct mpcb_problem`` (include/mpcb.h) for a :class:`Problem`.  Returns the ctypes struct and the list of numpy
+    arrays its pointers refer to (keep it alive as long as the struct is used)."""
+    p, st = problem, problem.settings
+    cp = _lib.MpcbProblem()
+    cp.Nx, cp.Nc, cp.Nb, cp.n, cp.m = p.Nx, p.Nc, p.Nb, p.n, p.m
+    cp.in_track, cp.delta_v, cp.is_reject, cp.has_noise = int(p.in_track), int(p.delta_v), int(p.is_reject), int(p.has_noise)
+    cp.noise_length = int(p.noise_length)
+    cp.estimator = int(p.estimator)
+    cp.rho0, cp.sigma, cp.alpha = st.rho, st.sigma, st.alpha
+    cp.eps_abs, cp.eps_rel, cp.eps_prim_inf = st.eps_abs, st.eps_rel, st.eps_prim_inf
+    cp.adaptive_rho_tolerance = st.adaptive_rho_tolerance
+    cp.max_iter, cp.check_termination = st.max_iter, st.check_termination
+    cp.adaptive_rho, cp.adaptive_rho_interval = int(st.adaptive_rho), st.adaptive_rho_interval
+    tables = []
+
+    def fixed(name, arr, cnt):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        assert a.size == cnt, (name, a.size, cnt)
+        getattr(cp, name)[:] = a.tolist()
+
+    fixed("Ad", p.Ad, 16); fixed("Bd", p.Bd, 8); fixed("Ao", p.Ao, 36); fixed("Bou", p.Bou, 12)
+    fixed("Qw", p.Qw, 36); fixed("Kpf", p.Kpf, 8); fixed("Kif", p.Kif, 2); fixed("xr", p.xr, 4)
+    cp.umax0, cp.r_p, cp.r_tol = p.umax0, p.r_p, p.r_tol
+    cp.suc_dist, cp.suc_ang_deg, cp.mean_mtn, cp.T = p.suc_dist, p.suc_ang, p.mean_mtn, p.T
+
+    def table(name, arr, dtype=np.float64):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        tables.append(a)
+        ptr_t = _lib.c_double_p if dtype == np.float64 else _lib.c_int32_p
+        setattr(cp, name, a.ctypes.data_as(ptr_t))
+
+    cp.has_debris, cp.scaling = int(p.has_debris), int(st.scaling)
+    if p.has_debris:
+        table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
+        cp.debris_center[:] = np.asarray(p.debris_center, float).tolist()
+        cp.debris_side, cp.debris_detect = float(p.debris_side), float(p.debris_detect)
+        cp.debris_verts[:] = np.asarray(p.debris_verts, float).reshape(-1).tolist()
+    else:
+        table("P_s", p.P_s); table("q_s", p.q_s); table("A_s", p.A_s); table("l_s", p.l_s); table("u_s", p.u_s)
+        table("D", p.D); table("E", p.E); table("ctype", p.ctype, np.int32); table("V", p.V); table("lam", p.lam)
+        # unscaled data as well: the multi-RHS (wave) solver block iterates in unscaled variables
+        table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
+    cp.K_dead[:] = np.asarray(p.K_dead, float).reshape(-1).tolist()
+    cp.Ki_dead[:] = np.asarray(p.Ki_dead, float).reshape(-1).tolist()
+    cp.c = p.c
+    return cp, tables
+
+
 class Engine:
     """``pin_outputs=True`` returns host results in page-locked arrays that the engine keeps and
     OVERWRITES on the next call with the same shapes (fast D2H for repeated batches; copy what you keep)."""
@@ -90,49 +139,7 @@ class Engine:
         self.device = int(device)
         self._h = C.c_void_p()
         self.B = 0
-        p, st = problem, problem.settings
-        cp = _lib.MpcbProblem()
-        cp.Nx, cp.Nc, cp.Nb, cp.n, cp.m = p.Nx, p.Nc, p.Nb, p.n, p.m
-        cp.in_track, cp.delta_v, cp.is_reject, cp.has_noise = int(p.in_track), int(p.delta_v), int(p.is_reject), int(p.has_noise)
-        cp.noise_length = int(p.noise_length)
-        cp.estimator = int(p.estimator)
-        cp.rho0, cp.sigma, cp.alpha = st.rho, st.sigma, st.alpha
-        cp.eps_abs, cp.eps_rel, cp.eps_prim_inf = st.eps_abs, st.eps_rel, st.eps_prim_inf
-        cp.adaptive_rho_tolerance = st.adaptive_rho_tolerance
-        cp.max_iter, cp.check_termination = st.max_iter, st.check_termination
-        cp.adaptive_rho, cp.adaptive_rho_interval = int(st.adaptive_rho), st.adaptive_rho_interval
-        self._tables = []
-
-        def fixed(name, arr, cnt):
-            a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
-            assert a.size == cnt, (name, a.size, cnt)
-            getattr(cp, name)[:] = a.tolist()
-
-        fixed("Ad", p.Ad, 16); fixed("Bd", p.Bd, 8); fixed("Ao", p.Ao, 36); fixed("Bou", p.Bou, 12)
-        fixed("Qw", p.Qw, 36); fixed("Kpf", p.Kpf, 8); fixed("Kif", p.Kif, 2); fixed("xr", p.xr, 4)
-        cp.umax0, cp.r_p, cp.r_tol = p.umax0, p.r_p, p.r_tol
-        cp.suc_dist, cp.suc_ang_deg, cp.mean_mtn, cp.T = p.suc_dist, p.suc_ang, p.mean_mtn, p.T
-
-        def table(name, arr, dtype=np.float64):
-            a = np.ascontiguousarray(arr, dtype=dtype)
-            self._tables.append(a)
-            ptr_t = _lib.c_double_p if dtype == np.float64 else _lib.c_int32_p
-            setattr(cp, name, a.ctypes.data_as(ptr_t))
-
-        cp.has_debris, cp.scaling = int(p.has_debris), int(st.scaling)
-        if p.has_debris:
-            table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
-            cp.debris_center[:] = np.asarray(p.debris_center, float).tolist()
-            cp.debris_side, cp.debris_detect = float(p.debris_side), float(p.debris_detect)
-            cp.debris_verts[:] = np.asarray(p.debris_verts, float).reshape(-1).tolist()
-        else:
-            table("P_s", p.P_s); table("q_s", p.q_s); table("A_s", p.A_s); table("l_s", p.l_s); table("u_s", p.u_s)
-            table("D", p.D); table("E", p.E); table("ctype", p.ctype, np.int32); table("V", p.V); table("lam", p.lam)
-            # unscaled data as well: the multi-RHS (wave) solver block iterates in unscaled variables
-            table("P_u", p.P); table("q_u", p.q); table("A_u", p.A); table("l_u", p.l); table("u_u", p.u)
-        cp.K_dead[:] = np.asarray(p.K_dead, float).reshape(-1).tolist()
-        cp.Ki_dead[:] = np.asarray(p.Ki_dead, float).reshape(-1).tolist()
-        cp.c = p.c
+        cp, self._tables = fill_problem_struct(problem)
         _lib.check(self.lib.mpcb_create(C.byref(cp), self.device, C.byref(self._h)))
 
     # ------------------------------------------------------------------ lifetime

@@ -18,6 +18,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+from . import _lib
 from .engine import Engine
 from .mpcsim import Noise
 from .problem import build_problem
@@ -58,6 +59,54 @@ def _run(sc, mp, fp, debris, x0, noise, device, philox=None):
         eng.close()
 
 
+class RatioSweep:
+    """``test/disturbRejComp.py:74-100`` as a prepared plan: one engine per (noise hold length, reject / no reject) cell, built
+    once, so that repeated sweeps (Monte-Carlo batches, benchmark steps) pay no set-up.  ``run`` takes the lanes' initial
+    states and one disturbance tensor per hold length (shared by the cell's two modes, lane by lane, which keeps the
+    reference's pairing of the rejection / no-rejection runs) and returns the ratio curve."""
+
+    def __init__(self, sim_conditions, mpc_params, fail_params, debris, noise_std: Sequence[float], noise_lengths: Sequence[float],
+                 device: int = 0, pin_outputs: bool = False, settings=None):
+        self.noise_lengths = [int(nl) for nl in noise_lengths]
+        self.noise_std = tuple(float(v) for v in noise_std)
+        self.nsteps = n_control_steps(sim_conditions)
+        self.device = device
+        self.engines = []                      # [length][mode]: mode 0 = no rejection, 1 = rejection
+        for nl in self.noise_lengths:
+            row = []
+            for rej in (False, True):
+                sc = copy.copy(sim_conditions)
+                sc.isReject = rej
+                sc.noise = Noise(self.noise_std, nl)
+                row.append(Engine(build_problem(sc, mpc_params, fail_params, debris, settings), device, pin_outputs=pin_outputs))
+            self.engines.append(row)
+
+    def refreshes(self, i: int) -> int:
+        return noise_refreshes(self.nsteps, self.noise_lengths[i])
+
+    def close(self):
+        for row in self.engines:
+            for e in row:
+                e.close()
+        self.engines = []
+
+    def run(self, x0, noises, record=()):
+        """``x0[4, B]`` and ``noises[i][R_i, 2, B]`` (numpy or torch CUDA, all of one kind) -> dict with ``dist_ratios[len]``,
+        the two mean curves, the summed statistics vectors ``stats[len][mode]`` (what ranks all-reduce) and ``qp_solves``."""
+        L = len(self.noise_lengths)
+        stats = np.zeros((L, 2, _lib.NSTATS))
+        for i in range(L):
+            for k in range(2):
+                stats[i, k] = self.engines[i][k].simulate_discrete(x0, noises[i], self.nsteps, record=record).stats_vec
+        return self.reduce(stats)
+
+    def reduce(self, stats: np.ndarray) -> dict:
+        """Ratio curve from (all-reduced) statistics: stats[..., 0] = sum of final distances, [..., 3] = lanes."""
+        mean = stats[:, :, 0] / np.maximum(stats[:, :, 3], 1.0)
+        return {"noise_lengths": np.asarray(self.noise_lengths, float), "mean_dist_norej": mean[:, 0], "mean_dist_rej": mean[:, 1],
+                "dist_ratios": mean[:, 1] / mean[:, 0], "stats": stats, "qp_solves": float(stats[:, :, 5].sum())}
+
+
 def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, noise_std: Sequence[float],
                                noise_lengths: Sequence[float], mc_num: int = 100, seed: int = 0, device: int = 0,
                                noise_rng: str = "numpy") -> dict:
@@ -65,26 +114,22 @@ def final_distance_ratio_sweep(sim_conditions, mpc_params, fail_params, debris, 
     (``disturbRejComp.py:85-98``).  Returns the ratios and both means; ``mc_num`` lanes per rank and setting.
     ``noise_rng="philox"``: draws come from the device generator (stream = seed + hold-length index, lanes offset by rank)."""
     x0 = np.tile(np.asarray(sim_conditions.x0, float)[:, None], (1, mc_num))
-    nsteps = n_control_steps(sim_conditions)
     rng = np.random.default_rng(seed + 7919 * _rank())
     sig = np.asarray(noise_std, float)
-    means = np.zeros((len(noise_lengths), 2))
-    for i, nl in enumerate(noise_lengths):
-        R = noise_refreshes(nsteps, int(nl))
-        noise = rng.standard_normal((R, 2, mc_num)) * sig[None, :, None] if noise_rng == "numpy" else None
-        sums = np.zeros(4)
-        for k, rej in enumerate((False, True)):
-            sc = copy.copy(sim_conditions)
-            sc.isReject = rej
-            sc.noise = Noise(tuple(noise_std), int(nl))
-            run = _run(sc, mpc_params, fail_params, debris, x0, noise, device,
-                       None if noise_rng == "numpy" else (R, seed + i, _rank() * mc_num))
-            sums[2 * k] = run.stats["sum_final_dist"]
-            sums[2 * k + 1] = run.stats["n_lanes"]
-        sums = _allreduce_sum(sums, device)
-        means[i] = [sums[0] / sums[1], sums[2] / sums[3]]
-    return {"noise_lengths": np.asarray(noise_lengths, float), "mean_dist_norej": means[:, 0], "mean_dist_rej": means[:, 1],
-            "dist_ratios": means[:, 1] / means[:, 0]}
+    plan = RatioSweep(sim_conditions, mpc_params, fail_params, debris, noise_std, noise_lengths, device)
+    try:
+        noises = []
+        for i in range(len(plan.noise_lengths)):
+            R = plan.refreshes(i)
+            if noise_rng == "numpy":
+                noises.append(rng.standard_normal((R, 2, mc_num)) * sig[None, :, None])
+            else:
+                noises.append(plan.engines[i][0].noise_fill(mc_num, R, seed + i, _rank() * mc_num))
+        out = plan.run(x0, noises)
+        stats = _allreduce_sum(out["stats"].reshape(-1), device).reshape(out["stats"].shape)
+        return plan.reduce(stats)
+    finally:
+        plan.close()
 
 
 def success_rate(sim_conditions, mpc_params, fail_params, debris, mc_num: int = 300, seed: int = 0, device: int = 0,

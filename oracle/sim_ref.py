@@ -352,9 +352,53 @@ def _legacy_draw():
     return np.random.normal(0, 1, 4)
 
 
+# --------------------------------------------------------------------------- the real package, if it is ever importable
+def real_osqp_available():
+    """SURVEY 8(c) / BASELINE.md section 3: osqp is not installable offline, so the oracle restates it.  If ``import osqp``
+    succeeds at run time the closed loop below can run on the REAL solver (``solver='osqp'``), which is the only way the
+    third-party boundary ever gets pinned; bench.py's reference arm switches to it and says so."""
+    try:
+        import osqp  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+class _RealOSQP:
+    """``osqp.OSQP`` behind the small protocol ``OSQPRef`` exposes (dense ``A`` on update -> the CSC value array the reference
+    passes as ``Ax``, trajectorySimulate.py:348)."""
+
+    def setup(self, P, q, A, l, u, **kw):
+        import osqp
+        from scipy import sparse
+        self._A = sparse.csc_matrix(A)
+        self._A.sort_indices()
+        self._rows, self._cols = self._A.nonzero()
+        order = np.lexsort((self._rows, self._cols))
+        self._rows, self._cols = self._rows[order], self._cols[order]
+        self._prob = osqp.OSQP()
+        self._prob.setup(sparse.triu(sparse.csc_matrix(P)).tocsc(), np.asarray(q, float), self._A, np.asarray(l, float),
+                         np.asarray(u, float), **kw)
+
+    def solve(self):
+        res = self._prob.solve()
+        res.info.rho = getattr(res.info, 'rho_estimate', float('nan'))
+        return res
+
+    def update(self, l=None, u=None, A=None):
+        kw = {}
+        if l is not None:
+            kw['l'] = np.asarray(l, float)
+        if u is not None:
+            kw['u'] = np.asarray(u, float)
+        if A is not None:
+            kw['Ax'] = np.asarray(A)[self._rows, self._cols].astype(float)
+        self._prob.update(**kw)
+
+
 # --------------------------------------------------------------------------- discrete
 def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, regen_sigmas=True,
-                        use_sympy=False, max_steps=None, chol_fail='raise', estimator='ukf'):
+                        use_sympy=False, max_steps=None, chol_fail='raise', estimator='ukf', solver='restated'):
     """trajectorySimulate.py:17-388.  Returns a SimRun-like namespace plus per-step solver
     telemetry (``status_val``, ``iters``, ``rho``, ``u_raw``) used by the parity tests."""
     if draw is None:
@@ -369,7 +413,7 @@ def trajectory_simulate(sc, mp, fp, debris, draw=None, solver_settings=None, reg
         nsim = min(nsim, max_steps)
     l, u = s.l.copy(), s.u.copy()
 
-    prob = OSQPRef()
+    prob = _RealOSQP() if solver == 'osqp' else OSQPRef()
     prob.setup(s.P, s.q, s.A, l, u, **dict(dict(warm_start=True, verbose=False), **(solver_settings or {})))
 
     xest0 = np.hstack([s.x0, 0., 0.])
