@@ -22,7 +22,10 @@ def _host(a):
     return np.asarray(a)
 
 
-def full_horizon_report(got, ref, u_bar=1e-4):
+RHO_DECISION_TOL = 1e-2
+
+
+def full_horizon_report(got, ref, u_bar=1e-4, rho_tol=RHO_DECISION_TOL):
     """``got``: BatchSimRun (engine layout ``[field, T, B]``); ``ref``: dict of ``simulate_discrete_batch``
     (``[T, B, field]``).  Returns a JSON-serialisable dict."""
     it_g, it_r = _host(got.iters).astype(np.int64), np.asarray(ref["iters"], np.int64)            # [nsim, B]
@@ -42,8 +45,10 @@ def full_horizon_report(got, ref, u_bar=1e-4):
     if rho_g is not None and rho_r is not None:
         # adaptive rho is a discrete decision too (OSQP adapts when the estimate leaves [rho/5, 5 rho]): a lane where one side
         # adapted and the other did not has diverged even while the iteration counts still coincide
+        # (RHO_DECISION_TOL: an adaptation multiplies rho by >= 5 or <= 1/5, so 1 % separates "adapted differently" from the
+        # 1e-9..1e-4 by which two float64 evaluations of sqrt(pri/dua) differ once the KKT system is ill-conditioned)
         with np.errstate(invalid="ignore"):
-            differ |= (np.abs(rho_g - rho_r) > 1e-6 * np.abs(rho_r)) & live
+            differ |= (np.abs(rho_g - rho_r) > rho_tol * np.abs(rho_r)) & live
     first = np.where(differ.any(axis=0), differ.argmax(axis=0), nsim)                               # first differing solve
     # a lane also diverges where the two sides stop at different steps
     first = np.where(term_g != term_r, np.minimum(first, np.minimum(term_g, term_r)), first)
@@ -97,6 +102,19 @@ def full_horizon_report(got, ref, u_bar=1e-4):
     rep["i_term_equal_frac"] = float((term_g == term_r).mean())
     rep["mean_final_pos_norm_oracle"] = float(np.nanmean(np.linalg.norm(fin_r[:, :2], axis=1)))
     return rep
+
+
+def as_engine_layout(ref):
+    """A ``simulate_discrete_batch`` / ``c_ref.simulate_discrete`` dict dressed as a BatchSimRun (``[field, T, B]``), so that
+    two CPU implementations can be compared with each other by ``full_horizon_report`` (the control of the parity tests)."""
+    from types import SimpleNamespace
+    B = len(ref["i_term"])
+    x = np.asarray(ref["x_true"])
+    fin = np.array([x[max(int(t) - 1, 0), b, :2] for b, t in enumerate(ref["i_term"])])
+    return SimpleNamespace(iters=ref["iters"], status=ref["status"], ctrlr_seq=ref["ctrlr_seq"], i_term=ref["i_term"],
+                           ctrl_hist=np.asarray(ref["ctrl_hist"]).transpose(2, 0, 1), x_true=x.transpose(2, 0, 1),
+                           rho=ref.get("rho_hist"), final_dist=ref.get("final_dist", np.linalg.norm(fin, axis=1)),
+                           isSuccess=np.asarray(ref.get("isSuccess", np.zeros(B, int))))
 
 
 def markdown_row(name, rep):

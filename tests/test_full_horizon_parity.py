@@ -4,11 +4,15 @@ What can and cannot be asserted (measured with tools/parity
 
 * The closed loop of the reference is chaotic at the level of OSQP's discrete decisions (terminate at this 25-iteration
   check or the next, adapt rho or not): the R = 0 UKF and the 1e-3 termination tolerances amplify a 1e-13 perturbation of
-  x0 into a different iteration count on ~15 % of config 2's lanes within 300 steps -- measured on the ORACLE AGAINST
-  ITSELF (the control below).  No two float64 implementations can do better than that floor.
-* Engine vs oracle with the SAME spectral tables (the device arithmetic in isolation): the first solve agrees to 4e-16,
-  lanes stay exact at the control's rate.  Engine vs oracle with the oracle's own tables adds the 1e-11..1e-9 by which two
-  `eigh` calls reconstruct M(rho)^-1, and loses a further ~13 % of config 2's lanes.
+  x0 into a different decision on ~13 % of config 2's lanes within 300 steps -- measured on the ORACLE AGAINST ITSELF (the
+  control below).  No two float64 implementations can do better than that floor, and the two CPU oracles (numpy
+  eigen-decomposition vs the C twin's Cholesky) agree with each other on 71 % of config 2's lanes
+  (tests/test_oracle_c.py::test_c_twin_full_horizon_against_the_batched_oracle, gpurun_out r2b_parity_rho_probe.json).
+* "Exact" = iteration count, OSQP status, controller choice and rho (to 1 %: did both sides adapt, oracle/parity.py) of
+  EVERY solve up to i_term, and i_term itself.  Measured (seed 4321; engine's tables / oracle's own tables):
+  config 2 82 % / 63 %, config 2 quiet 99 % / 96 %, config 4 99 % / 97 %, config 5 cell 83 % / 73 %.  Engine vs oracle with
+  the SAME spectral tables isolates the device arithmetic (it stays exact at the control's rate); the oracle's own tables
+  add the 1e-11..1e-9 by which two `eigh` calls reconstruct M(rho)^-1.
 * Until a lane's first differing decision, controls agree far inside the task's 1e-4 bar; that is asserted exactly.
 """
 import numpy as np
@@ -17,7 +21,7 @@ import pytest
 import mpc_arpo_project_b200 as M
 from mpc_arpo_project_b200.presets import WORKLOADS, make_inputs, make_params
 from oracle.batched_ref import simulate_discrete_batch
-from oracle.parity import full_horizon_report
+from oracle.parity import as_engine_layout, full_horizon_report
 from oracle.sim_ref import trajectory_simulate_c
 
 pytestmark = pytest.mark.gpu
@@ -25,9 +29,9 @@ pytestmark = pytest.mark.gpu
 U_BAR = 1e-4          # BASELINE.json north_star: per-step controls within 1e-4 abs
 # name: (lanes, floor on exact lanes with the engine's tables, floor with the oracle's own tables, bound on |du| over the exact prefix)
 CASES = {
-    "config2": (256, 0.75, 0.58, 1e-6),
-    "config2_quiet": (256, 0.96, 0.95, 1e-6),
-    "config4": (192, 0.93, 0.92, 1e-6),
+    "config2": (256, 0.72, 0.53, 1e-6),
+    "config2_quiet": (256, 0.95, 0.90, 1e-6),
+    "config4": (192, 0.95, 0.90, 1e-6),
     "config5_cell": (128, 0.72, 0.62, 1e-6),
 }
 
@@ -80,8 +84,7 @@ def test_engine_is_as_faithful_as_the_oracle_is_to_itself():
     rng = np.random.default_rng(99)
     x0p = np.ascontiguousarray((x0 * (1 + 1e-13 * rng.standard_normal(x0.shape))).T)
     refp = simulate_discrete_batch(sc, mp, fp, x0p, noise, chol_fail='clamp', spectral=(prob.V, prob.lam))
-    same = ((refp["iters"] == ref["iters"]) & (refp["status"] == ref["status"])).all(axis=0) & (refp["i_term"] == ref["i_term"])
-    control = float(same.mean())
+    control = full_horizon_report(as_engine_layout(refp), ref, U_BAR)["exact_frac"]
     rep = full_horizon_report(got, ref, U_BAR)
     print("control (oracle vs oracle, x0 * (1 + 1e-13)):", control, "engine vs oracle:", rep["exact_frac"])
     assert control < 0.999, "the control found no sensitivity: the floor argument of DESIGN.md section 4 would not hold"

@@ -81,3 +81,26 @@ def test_c_twin_matches_reference_driver_fixture(name):
     np.testing.assert_allclose(r["x_est"][:it + 1, 0].T, g["x_est"][:, :it + 1], rtol=1e-7, atol=1e-6)
     np.testing.assert_array_equal(r["ctrlr_seq"][:it, 0].astype(float), g["ctrlr_seq"])
     assert bool(r["isSuccess"][0]) == bool(g["isSuccess"])
+
+
+def test_c_twin_full_horizon_against_the_batched_oracle():
+    """All 300 control steps of config 2's lanes: two CPU implementations with independent linear algebra (numpy
+    eigen-decomposition of M(rho) vs the twin's dense Cholesky).  The closed loop is chaotic in OSQP's discrete decisions
+    (tests/test_full_horizon_parity.py), so the two agree on a FRACTION of the lanes to the end -- this is the floor any
+    float64 implementation, the CUDA engine included, is measured against -- and to the task's 1e-4 in the controls until a lane's first
+    differing decision."""
+    from mpc_arpo_project_b200.presets import WORKLOADS, make_inputs
+    from oracle.parity import as_engine_layout, full_horizon_report
+    wl = WORKLOADS["config2"]
+    sc, mp, fp, _ = make_params(wl["case"])
+    B = 96
+    x0, noise = make_inputs(wl, B, 4321)
+    prob = M.build_problem(sc, mp, fp, None)
+    twin = c_ref.simulate_discrete(prob, x0, noise, 300, nthreads=0)
+    ref = simulate_discrete_batch(sc, mp, fp, np.ascontiguousarray(x0.T), noise, chol_fail='clamp')
+    rep = full_horizon_report(as_engine_layout(twin), ref)
+    print("C twin vs numpy oracle, config 2, 300 steps:", rep["exact_lanes"], "/", B, "max du on prefix", rep["max_du_prefix"])
+    assert 0.45 <= rep["exact_frac"] < 1.0, rep           # measured 0.62 on 256 lanes; 1.0 would mean no sensitivity to show
+    assert rep["max_du_prefix"] <= 1e-4, rep             # the task's bar; measured 1.2e-5 (Cholesky vs spectral solve at rho ~ 1e4+)
+    assert rep["solves_exact_prefix"] >= 0.75 * rep["solves_compared"], rep
+    assert rep["i_term_equal_frac"] >= 0.9
