@@ -9,8 +9,9 @@ workload (config2 = 4096 linear-CW radial trajectories, 10-step horizon, 300 con
 per live trajectory per control step; config5 = the whole disturbRejComp sweep, 10 hold lengths x
 {reject, no reject}).  Every step draws NEW lanes: seed = 1234 + step * world + rank, so N = 1 and
 N = 8 see the same lane distribution and no figure rests on one lucky seed.  For N > 1 the driver
-launches this file under torchrun; every rank runs its own shard of lanes (weak scaling) and the
-only collective is an NCCL all-reduce of the MPCB_NSTATS final statistics, inside the timed region.
+launches this file under torchrun; every rank runs its own shard of lanes (weak scaling), steps do
+not synchronise the ranks, and the only collective is ONE NCCL all-reduce of the accumulated
+MPCB_NSTATS statistics after the last step, inside the timed region.
 
 Prints ONE JSON line on rank 0 (see README / DESIGN.md section "Measurement").
 """
@@ -210,9 +211,8 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    lanes = max(cores, args.ref_lanes)
-    if wl["kind"] == "S":
-        lanes = max(lanes, 20)
+    lanes = args.ref_lanes or (cores if wl["kind"] == "C" else (10 * cores if wl["kind"] == "S" else 128 * cores))
+    lanes = max(cores, lanes)
     times, solves, kind, desc = [], 0, "port", ""
     for i in range(args.warmup + args.steps):
         s, w, kind, desc = cpu_arm(wl, lanes, cores, SEED0 + i)
@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=None, help="lanes per GPU (default: the workload's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-lanes", type=int, default=256, help="reference arm: lanes per step")
+    ap.add_argument("--ref-lanes", type=int, default=0, help="reference arm: lanes per step (0: 128 per core, 1 per core for the continuous simulator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-lanes", type=int, default=64, help="lanes of the full-horizon parity slice (0 = skip)")
     args = ap.parse_args()
@@ -347,28 +347,33 @@ def main():
 
     def timed(first, nrep, on_device):
         """nrep steps starting at input index `first`; returns (device ms summed over steps, solves, last result).  L2 is
-        flushed between steps.  The statistics all-reduce -- the path's only collective -- is INSIDE the timed region: e1 is
-        recorded on torch's stream after the collective, which itself waits for the engine's stream."""
+        flushed between steps.  Ranks run their steps independently (lanes are independent; a Monte-Carlo job needs its
+        statistics once, at the end): the all-reduce of the accumulated MPCB_NSTATS statistics -- the path's only collective --
+        follows the last step INSIDE the timed region: its event pair is recorded on torch's stream, which NCCL runs on."""
         tot_ms, solves, res = 0.0, 0, None
         cur = torch.cuda.current_stream(dev)
+        acc = np.zeros((len(engines), _lib.NSTATS))
         for k in range(nrep):
             flush.fill_(1)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             sv, st, res = step(first + k, on_device)
-            if world > 1:
-                stats_t.copy_(torch.from_numpy(np.ascontiguousarray(st)), non_blocking=True)
-                cur.wait_stream(stream)
-                dist.all_reduce(stats_t)
-                e1.record(cur)
-            else:
-                e1.record(stream)
+            e1.record(stream)
             torch.cuda.synchronize(dev)
             tot_ms += e0.elapsed_time(e1)
+            acc += st
             if os.environ.get("BENCH_VERBOSE"):
                 print(f"[bench] step {first + k} (seed {SEED0 + (first + k) * world + rank}): {e0.elapsed_time(e1):.2f} ms, {sv} solves", file=sys.stderr)
             solves += sv
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            stats_t.copy_(torch.from_numpy(np.ascontiguousarray(acc)), non_blocking=True)
+            dist.all_reduce(stats_t)
+            e1.record(cur)
+            torch.cuda.synchronize(dev)
+            tot_ms += e0.elapsed_time(e1)       # includes the wait for the slowest rank: max over ranks is taken below anyway
         return tot_ms, solves, res
 
     # the sampler starts BEFORE the warm-up: nvidia-smi's own start-up stalls the GPU it queries
@@ -522,7 +527,7 @@ def main():
             line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            lanes = 16 * cores if kind != "C" else 2 * cores
+            lanes = 512 * cores if kind == "D" else (20 * cores if kind == "S" else 2 * cores)     # ~10-20 s of CPU work
             s, w, ckind, desc = cpu_arm(wl, lanes, cores, SEED0)
             cb = {"value": s / w, "unit": UNIT, "cores": cores, "kind": ckind,
                   "sample": f"{lanes} lanes of {args.workload}, full horizon, {w:.1f} s wall: {desc}"}

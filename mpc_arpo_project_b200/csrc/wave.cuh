@@ -39,7 +39,9 @@
 #define WAVE_NT 11        // 8-wide tiles
 #define WAVE_LD 84        // stride of Vp rows and of the tile's n-vector rows: 4 (mod 16) keeps both fragment patterns conflict free
 #define WAVE_LDV 52       // stride of the dynamics-dual exchange rows (48 used)
+#ifndef WAVE_WARPS
 #define WAVE_WARPS 8
+#endif
 #define WAVE_NVS 28       // variable slots per thread: x 3x4, u 2x2, s 2x5, d 2
 #define WAVE_NRS 43       // row slots per thread: dyn 3x4, los 3x5, box-u 2x2, box-s 2x5, pin 2
 #define WAVE_INF 1e30
