@@ -84,6 +84,8 @@ class BatchedQP:
         self.u = np.tile(ut, (B, 1))
         self.variant = np.zeros(B, int)
         self.flip_flag = np.zeros(B, bool)
+        self.eqm = np.zeros((B, self.row3.size), bool)       # per lane: which velocity-bound rows are equalities right now
+        self.retype = True
         self.dy = np.zeros((B, self.m))
         self.is_reject = 1.0
 
@@ -92,13 +94,21 @@ class BatchedQP:
         E = self.E
         self.l[idx, :4] = self.u[idx, :4] = -xhat4 * E[:4]
         self.u[np.ix_(idx, self.row3)] = val[:, None] * E[self.row3][None, :]
-        self.flip_flag[idx] |= (val[:, None] * E[self.row3][None, :] < RHO_TOL).any(axis=1)
+        eq = val[:, None] * E[self.row3][None, :] - self.lt[self.row3][None, :] < RHO_TOL
+        self.flip_flag[idx] |= eq.any(axis=1)
+        if self.retype:
+            # OSQP update_rho_vec (auxil.c): a row whose scaled bounds come within RHO_TOL of each other is re-classified as an
+            # equality (rho_vec = 1e3 rho) and the KKT matrix refactored; it returns to an inequality when they part again
+            self.eqm[idx] = eq
         self.l[idx, -2:] = self.u[idx, -2:] = self.is_reject * dhat2 * E[-2:]
         self.variant[idx] = variant
 
-    def _rho_vecs(self, rho):
+    def _rho_vecs(self, rho, g=None):
         rv = np.where(self.ctype[None, :] == -1, RHO_MIN,
                       np.where(self.ctype[None, :] == 1, RHO_EQ_OVER_RHO_INEQ * rho[:, None], rho[:, None]))
+        if g is not None and self.eqm[g].any():
+            sub = rv[:, self.row3]
+            rv[:, self.row3] = np.where(self.eqm[g], RHO_EQ_OVER_RHO_INEQ * rho[:, None], sub)
         return rv, 1.0 / rv
 
     def solve(self, idx):
@@ -142,12 +152,22 @@ class BatchedQP:
         st = self.st
         A, V, lam = self.Av[v], self.V[v], self.lam[v]
         x, z, y = self.x[g], self.z[g], self.y[g]
-        rv, rinv = self._rho_vecs(self.rho[g])
+        rv, rinv = self._rho_vecs(self.rho[g], g)
         dscale = 1.0 / (1.0 + self.rho[g][:, None] * lam[None, :])
         l, u = self.l[g], self.u[g]
+        # re-typed rows F of a lane add (1e3 - 1) rho a_i a_i' to M(rho): Woodbury on the spectral inverse S,
+        #   (M + A_F' D A_F)^-1 = S - S A_F' (D^-1 + A_F S A_F')^-1 A_F S,  D = 999 rho I
+        wood = []
+        for k in np.nonzero(self.eqm[g].any(axis=1))[0]:
+            AF = A[self.row3[self.eqm[g[k]]]]                                   # [f, n]
+            U = (V * dscale[k][None, :]) @ (V.T @ AF.T)                         # S A_F'  [n, f]
+            C = np.linalg.inv(np.eye(AF.shape[0]) / ((RHO_EQ_OVER_RHO_INEQ - 1.0) * self.rho[g[k]]) + AF @ U)
+            wood.append((k, AF, U @ C))
         for _ in range(niter):
             r = st['sigma'] * x - self.q[None, :] + (rv * z - y) @ A
             xt = ((r @ V) * dscale) @ V.T
+            for k, AF, UC in wood:
+                xt[k] = xt[k] - UC @ (AF @ xt[k])
             zt = xt @ A.T
             x = st['alpha'] * xt + (1 - st['alpha']) * x
             zr = st['alpha'] * zt + (1 - st['alpha']) * z
@@ -202,7 +222,7 @@ class BatchedQP:
 
 
 def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=None, regen_sigmas=True, nsteps=None,
-                            chol_fail='raise', spectral=None):
+                            chol_fail='raise', spectral=None, retype=True):
     """Batched ``trajectorySimulate`` (debris-free).  ``x0_batch[B,4]``; ``noise_batch[R,2,B]``
     holds sigma-scaled position disturbances, refreshed every ``noise_length`` steps
     (R >= nsim//noise_length + 1).  Returns a dict of SoA arrays."""
@@ -212,6 +232,7 @@ def simulate_discrete_batch(sc, mp, fp, x0_batch, noise_batch=None, settings=Non
     s = build_setup(sc0, mp, fp, None)
     nsim = int(sc.T_final / sc.time_stp) if nsteps is None else nsteps
     qp = BatchedQP(s, B, settings, spectral=spectral)
+    qp.retype = retype          # False: the pre-round-2 behaviour (re-typed rows only flagged), kept for the sensitivity check in the tests
     qp.is_reject = 1.0 if sc.isReject else 0.0
     has_noise = sc.noise is not None
     nrep = s.noiseRepeat

@@ -36,6 +36,7 @@
 #define RHO_MIN 1e-6
 #define RHO_MAX 1e6
 #define RHO_EQ 1e3
+#define RHO_TOL 1e-4
 #define DIV_TOL 1e-30
 #define UKF_NPL 0.05
 #define UKF_WM0 (-5.95 / 0.05)
@@ -54,7 +55,9 @@ typedef struct {
 typedef struct {
   double *x, *z, *y, *l, *u, *dy, *rv, *rinv, *av, *M, *rhs, *xt, *zt, *Ax, *Px, *Aty, *t1;
   double rho, f_rho;
-  int f_var;             /* (rho, variant) the factor in M was built for */
+  int f_var;             /* (rho, variant, re-typed rows) the factor in M was built for */
+  unsigned eqmask, f_eqmask;   /* bit k: the velocity-bound row of stage k is currently an EQUALITY for OSQP (u - l < RHO_TOL after
+                                  scaling, osqp auxil.c update_rho_vec: rho_vec[i] = 1e3 rho and the KKT matrix is refactored) */
 } work_t;
 
 static void csr_mv(const shared_t *S, const double *av, const double *x, double *out) {
@@ -108,10 +111,16 @@ static void chol_solve(const double *L, int n, double *b) {
 }
 
 static void set_rho_vec(const mpcb_problem *p, work_t *w) {
+  const int nX = 4 * (p->Nx + 1);
   for (int i = 0; i < p->m; ++i) {
     w->rv[i] = p->ctype[i] == -1 ? RHO_MIN : (p->ctype[i] == 1 ? RHO_EQ * w->rho : w->rho);
     w->rinv[i] = 1.0 / w->rv[i];
   }
+  for (int k = 0; k <= p->Nb && k < 32; ++k)
+    if (w->eqmask & (1u << k)) {
+      w->rv[nX + 5 * k + 3] = RHO_EQ * w->rho;
+      w->rinv[nX + 5 * k + 3] = 1.0 / w->rv[nX + 5 * k + 3];
+    }
 }
 
 /* prob.solve(): returns OSQP status_val, *iters_out = info.iter */
@@ -130,11 +139,12 @@ static int solve(const mpcb_problem *p, const shared_t *S, work_t *w, int varian
   int it = 0, status = MPCB_QP_UNSOLVED;
   set_rho_vec(p, w);
   while (it < p->max_iter) {
-    if (w->f_rho != w->rho || w->f_var != variant) {
+    if (w->f_rho != w->rho || w->f_var != variant || w->f_eqmask != w->eqmask) {
       set_rho_vec(p, w);
       if (factor(S, w) != 0) return MPCB_QP_UNSOLVED;
       w->f_rho = w->rho;
       w->f_var = variant;
+      w->f_eqmask = w->eqmask;
     }
     for (int k = 0; k < p->check_termination; ++k) {
       for (int i = 0; i < m; ++i) w->t1[i] = w->rv[i] * w->z[i] - w->y[i];
@@ -320,7 +330,12 @@ static int set_params(const mpcb_problem *p, work_t *w, const double *xe) {
   const int m = p->m, nX = 4 * (p->Nx + 1);
   for (int i = 0; i < 4; ++i) w->l[i] = w->u[i] = -xe[i] * p->E[i];
   const double val = fabs(xe[0] - p->xr[0]) + fabs(xe[1] - p->xr[1]);
-  for (int k = 0; k <= p->Nb; ++k) w->u[nX + 5 * k + 3] = val * p->E[nX + 5 * k + 3];
+  w->eqmask = 0;
+  for (int k = 0; k <= p->Nb; ++k) {
+    const int r = nX + 5 * k + 3;
+    w->u[r] = val * p->E[r];
+    if (k < 32 && w->u[r] - w->l[r] < RHO_TOL) w->eqmask |= 1u << k;          /* row re-typing */
+  }
   for (int i = 0; i < 2; ++i) w->l[m - 2 + i] = w->u[m - 2 + i] = (p->is_reject ? xe[4 + i] : 0.0) * p->E[m - 2 + i];
   return (xe[2] >= 0 ? 0 : 1) + (xe[3] >= 0 ? 0 : 2);
 }
@@ -373,6 +388,7 @@ static void *worker(void *arg) {
       w.rho = fmin(fmax(p->rho0, RHO_MIN), RHO_MAX);
       w.f_rho = -1.0;
       w.f_var = -1;
+      w.eqmask = w.f_eqmask = 0;
       double xt[4], xe[6], ux[6], uP[36], xstore[4], unext[2] = {0, 0}, nz[2] = {0, 0}, xfin[4], xintf = 0.0;
       for (int k = 0; k < 4; ++k) { xt[k] = x0[(size_t)k * B + b]; xe[k] = xt[k]; xstore[k] = xt[k]; xfin[k] = NAN; }
       xe[4] = xe[5] = 0.0;

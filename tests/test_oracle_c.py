@@ -104,3 +104,21 @@ def test_c_twin_full_horizon_against_the_batched_oracle():
     assert rep["max_du_prefix"] <= 1e-4, rep             # the task's bar; measured 1.2e-5 (Cholesky vs spectral solve at rho ~ 1e4+)
     assert rep["solves_exact_prefix"] >= 0.75 * rep["solves_compared"], rep
     assert rep["i_term_equal_frac"] >= 0.9
+
+
+def test_c_twin_models_row_retyping():
+    """Lanes parked next to the target (tests/test_batched_ref.py::retype_lanes): the twin refactors with rho_vec = 1e3 rho on
+    the re-typed rows exactly as OSQP's update_rho_vec does, and agrees with the Woodbury form of the numpy oracle."""
+    from test_batched_ref import retype_lanes
+    case, x0, noise = retype_lanes()
+    sc, mp, fp, _ = make_params(case)
+    prob = M.build_problem(sc, mp, fp, None)
+    nsim = int(case["T_final"] / 0.5)
+    got = c_ref.simulate_discrete(prob, np.ascontiguousarray(x0.T), noise, nsim, nthreads=4)
+    ref = simulate_discrete_batch(sc, mp, fp, x0, noise, chol_fail='clamp')
+    assert ref["flip_flag"].sum() >= 6
+    assert np.array_equal(got["i_term"], ref["i_term"]) and np.array_equal(got["iters"], ref["iters"])
+    assert np.array_equal(got["status"], ref["status"])
+    for b in range(x0.shape[0]):
+        T = int(ref["i_term"][b])
+        np.testing.assert_allclose(got["ctrl_hist"][:T + 1, b], ref["ctrl_hist"][:T + 1, b], rtol=0, atol=1e-5)
