@@ -440,9 +440,11 @@ def main():
         wlp = wl if kind == "D" else dict(wl, kind="D")
         x0p, nzp = make_inputs(wlp, pl, SEED0 - 1)
         x0T = np.ascontiguousarray(x0p.T)
-        with M.Engine(prob, device=local) as pe:
-            got = M.trajectorySimulateBatch(sc if kind == "D" else plan_sc(sc), mp, fp, None, x0T, nzp, engine=pe)
-        ref = simulate_discrete_batch(sc if kind == "D" else plan_sc(sc), mp, fp, x0T, nzp, chol_fail="clamp", spectral=(prob.V, prob.lam))
+        psc = sc if kind == "D" else plan_sc(sc)
+        pprob = prob if kind == "D" else M.build_problem(psc, mp, fp, None)
+        with M.Engine(pprob, device=local) as pe:
+            got = M.trajectorySimulateBatch(psc, mp, fp, None, x0T, nzp, engine=pe)
+        ref = simulate_discrete_batch(psc, mp, fp, x0T, nzp, chol_fail="clamp", spectral=(pprob.V, pprob.lam))
         rep = full_horizon_report(got, ref)
         parity = {"lanes": rep["lanes"], "steps": rep["steps"], "exact_frac": rep["exact_frac"], "max_du": rep["max_du_prefix"],
                   "solves_on_exact_prefix": rep["solves_exact_prefix"], "solves_compared": rep["solves_compared"],
@@ -527,12 +529,17 @@ def main():
             line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            lanes = 512 * cores if kind == "D" else (20 * cores if kind == "S" else 2 * cores)     # ~10-20 s of CPU work
+            if kind == "C":
+                lanes = 2 * cores
+            else:       # a pilot sizes the sample to ~12 s of wall time on all cores (the families differ 40x in cost per solve)
+                pilot = (2 if kind == "D" else 1) * cores * (20 if kind == "S" else 1)
+                s0, w0 = cpu_twin_run(wl, pilot, cores, SEED0 - 7)
+                lanes = int(min(65536, max(pilot, pilot * 12.0 / max(w0, 1e-3))))
             s, w, ckind, desc = cpu_arm(wl, lanes, cores, SEED0)
             cb = {"value": s / w, "unit": UNIT, "cores": cores, "kind": ckind,
                   "sample": f"{lanes} lanes of {args.workload}, full horizon, {w:.1f} s wall: {desc}"}
             if kind != "C":
-                s1, w1 = cpu_twin_run(wl, max(2, lanes // cores), 1, SEED0)
+                s1, w1 = cpu_twin_run(wl, max(2 if kind == "D" else 20, lanes // (3 * cores)), 1, SEED0)
                 cb["one_core"] = s1 / w1
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

@@ -6,16 +6,37 @@
 // its Ruiz equilibration from scratch and refactors the KKT matrix, so nothing can be shared across
 // lanes or steps.  One CTA owns one lane and does, per control step, what OSQP does on the host:
 //   geometry -> A values -> scale_data (10 Ruiz passes) -> bounds, constraint types, rho vector ->
-//   M = P + sigma I + A' diag(rho_vec) A  (dense, global scratch) -> S = M^-1 (in-place Gauss-Jordan) ->
-//   ADMM with x~ = S r read from L2, termination / infeasibility / adaptive rho as in team.cuh ->
+//   M = P + sigma I + A' diag(rho_vec) A -> S = M^-1 (in-place Gauss-Jordan) -> ADMM with x~ = S r,
+//   termination / infeasibility / adaptive rho as in team.cuh ->
 //   controller select incl. the deadbeat avoidance law (:299-304), clip, plant, UKF, telemetry.
-// Throughput is not the goal here (the shared-operator kernels cover the debris-free families); parity
-// with the oracle's scalar path is (tests/test_gpu_parity.py::test_debris_*).
+//
+// The operator never leaves the SM.  Thread i owns ROW i of the n x n matrix (n <= 201): its first GEN_TMD = 128 entries
+// live in TENSOR MEMORY (256 32-bit columns of the thread's own TMEM lane, shape 32x32b: a second register file, as in
+// team.cuh -- there is no f64 tcgen05.mma), the rest in shared memory ([column][thread], conflict free).  Assembly, the
+// Gauss-Jordan sweeps (pivot row broadcast through a double-buffered shared row; the owner of row k+1 publishes it while
+// it applies pivot k, so a sweep costs two barriers) and the mat-vec all run on a thread's own row.  The first version of
+// this kernel kept M in a global scratch matrix and spent ~90 % of a solve in L2 round trips of the sweeps
+// (n^3 read-modify-writes per inverse): 4.6 k solves/s at Nx = 40.
+// Parity with the oracle's scalar path: tests/test_gpu_parity.py::test_debris_*.
 #pragma once
 #include "common.cuh"
 #include "sim.cuh"
+#include "team.cuh"      // tensor-memory load / store wrappers
 
 #define GEN_THREADS 256
+// Optional cycle breakdown (-DGEN_PROFILE): thread 0 of every CTA accumulates clock64() deltas into tot[4..10]:
+// 4 values + scaling, 5 assembly, 6 inversion, 7 iterations, 8 checks, 9 rest of the control step, 10 total.
+#ifdef GEN_PROFILE
+#define GP_DECL long long gp_t = clock64(); const long long gp_start = gp_t; long long gp_acc[6] = {0, 0, 0, 0, 0, 0};
+#define GP_MARK(k) { const long long gp_n = clock64(); gp_acc[k] += gp_n - gp_t; gp_t = gp_n; }
+#define GP_FLUSH if (tid == 0) { for (int q = 0; q < 6; ++q) atomicAdd(&a.tot[4 + q], (unsigned long long)gp_acc[q]); \
+                                 atomicAdd(&a.tot[10], (unsigned long long)(clock64() - gp_start)); }
+#else
+#define GP_DECL
+#define GP_MARK(k)
+#define GP_FLUSH
+#endif
+#define GEN_TMD 128        // doubles of a row of S kept in tensor memory (2 x 128 = 256 columns; 8 warps x 256 = the SM's 512 x 4)
 
 struct GenArgs {
   int n, m, nX, Nx, Nb, Nc, uoff, B, nnzA, nnzP, scaling;
@@ -42,7 +63,6 @@ struct GenArgs {
   double *xs, *zs, *ys, *rho, *u0;
   int *iter, *status;
   int warm;
-  double *scratch;            // [grid][n*n] dense operator per CTA
   int *queue;
   unsigned long long *tot;
   double *stats;
@@ -105,15 +125,38 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
   // ---- shared memory: vectors of length n / m, scaled values, reductions, lane context
   double *p = reinterpret_cast<double *>(gsm);
   auto take = [&](int cnt) { double *r = p; p += (cnt + 1) & ~1; return r; };
-  double *x = take(n), *xt = take(n), *rb = take(n), *qs = take(n), *D = take(n), *Dinv = take(n), *cmax = take(n);
+  double *x = take(n), *xt = take(n), *rb = take(n + 4), *qs = take(n), *D = take(n), *Dinv = take(n), *cmax = take(n);
   double *z = take(m), *y = take(m), *v = take(m), *dyb = take(m), *lo = take(m), *hi = take(m), *rv = take(m), *E = take(m),
          *Einv = take(m), *rmax = take(m);
   double *As = take(nnzA), *Ps = take(nnzP), *red = take(16 * NW), *fcol = take(n);
   int *ctype = reinterpret_cast<int *>(take((m + 1) / 2 + 1));
+  // operator storage: row tid of S = tmd doubles in tensor memory + (npad - tmd) in Sx[.][tid]; rowb = two pivot-row buffers
+  const int npad = (n + 3) & ~3, tmd = npad < GEN_TMD ? npad : GEN_TMD, TS = (n + 31) & ~31;
+  double *rowb = take(2 * npad), *Sx = take((npad - tmd) * TS);
   GenLane &L = *reinterpret_cast<GenLane *>(p);
   __shared__ int s_lane;
   __shared__ double s_c;
-  double *S = a.scratch + (size_t)blockIdx.x * n * n;
+  __shared__ uint32_t s_tmem;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t taddr = s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(2 * GEN_TMD * (warp >> 2));
+  if (tid < 4) rb[n + tid] = 0.0;        // the mat-vec reads r in chunks of four: the padding multiplies zero columns of S
+  const bool own = tid < n;              // owns a row of S (every thread still executes the warp-collective TMEM ops)
+  // entry j of the thread's own row (j uniform across the warp)
+  auto row_get = [&](int j) -> double {
+    if (j < tmd) {
+      uint32_t c4[4];
+      tmem_ld4(taddr + 2 * (j & ~1), c4);
+      tmem_wait_ld4(c4);
+      return (j & 1) ? u2d(c4[2], c4[3]) : u2d(c4[0], c4[1]);
+    }
+    return own ? Sx[(size_t)(j - tmd) * TS + tid] : 0.0;
+  };
 
   auto team_max = [&](double val) -> double {
     val = warp_max_nonneg(val);
@@ -147,6 +190,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
   };
 
   unsigned long long my_iters = 0, my_rebuilds = 0;
+  GP_DECL
   while (true) {
     __syncthreads();
     if (tid == 0) s_lane = atomicAdd(a.queue, 1);
@@ -286,65 +330,162 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         ctype[i] = fr ? -1 : ((u_ - l_ < MPCB_RHO_TOL) ? 1 : 0);
       }
       __syncthreads();
+      GP_MARK(0)
       int iter = 0, st = -10;
       bool need_op = true;                                        // update(Ax) always refactors
 
       while (st == -10) {
         if (need_op) {
           for (int i = tid; i < m; i += T) rv[i] = ctype[i] == -1 ? MPCB_RHO_MIN : (ctype[i] == 1 ? MPCB_RHO_EQ * rho : rho);
-          // M = P + sigma I + A' diag(rho_vec) A, entry by entry in a FIXED summation order (rows ascending: the two CSC
-          // columns are merged), so a lane's iterates do not depend on the order atomics happen to land in
+          // M = P + sigma I + A' diag(rho_vec) A = sum over rows r of rho_vec_r a_r a_r'.  Thread i builds row i of M in a
+          // thread-local array: for every row r of A that touches column i (CSC list, ascending r: a FIXED summation order)
+          // it adds rho_vec_r A_ri A_rj for the entries j of that row, then the row goes to tensor / shared memory four
+          // entries at a time.  (Merging column i with every column j instead costs the two disturbance columns, which
+          // touch all 4 (Nx + 1) dynamics rows, 35 k steps per assembly.)
           __syncthreads();
-          for (int o = tid; o < n * n; o += T) {
-            const int ci = o / n, cj = o - ci * n;
-            int ea = a.colptr[ci], eb = a.colptr[cj];
-            const int ea1 = a.colptr[ci + 1], eb1 = a.colptr[cj + 1];
-            double acc = (ci == cj) ? a.sigma : 0.0;
-            while (ea < ea1 && eb < eb1) {
-              const int ra = a.rowidx[ea], rb_ = a.rowidx[eb];
-              if (ra == rb_) {
-                acc = fma(rv[ra] * As[a.cscpos[ea]], As[a.cscpos[eb]], acc);
-                ++ea;
-                ++eb;
-              } else if (ra < rb_) {
-                ++ea;
-              } else {
-                ++eb;
+          {
+            double Mrow[GEN_THREADS];      // n <= GEN_THREADS; local memory (L1 / L2), dynamic index
+            for (int j = 0; j < npad; ++j) Mrow[j] = 0.0;
+            if (own) {
+              Mrow[tid] = a.sigma;
+              for (int ea = a.colptr[tid]; ea < a.colptr[tid + 1]; ++ea) {
+                const int r = a.rowidx[ea];
+                const double w = rv[r] * As[a.cscpos[ea]];
+                for (int e = a.rowptr[r]; e < a.rowptr[r + 1]; ++e) {
+                  const int j = a.colidx[e];
+                  Mrow[j] = fma(w, As[e], Mrow[j]);
+                }
+              }
+              for (int pe = a.prowptr[tid]; pe < a.prowptr[tid + 1]; ++pe) Mrow[a.pcol[pe]] += Ps[pe];
+            }
+            for (int j0 = 0; j0 < npad; j0 += 4) {
+              if (j0 < tmd) {
+                const uint32_t w8[8] = {(uint32_t)__double2loint(Mrow[j0]), (uint32_t)__double2hiint(Mrow[j0]),
+                                        (uint32_t)__double2loint(Mrow[j0 + 1]), (uint32_t)__double2hiint(Mrow[j0 + 1]),
+                                        (uint32_t)__double2loint(Mrow[j0 + 2]), (uint32_t)__double2hiint(Mrow[j0 + 2]),
+                                        (uint32_t)__double2loint(Mrow[j0 + 3]), (uint32_t)__double2hiint(Mrow[j0 + 3])};
+                tmem_st8(taddr + 2 * j0, w8);
+              } else if (own) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Sx[(size_t)(j0 + q - tmd) * TS + tid] = Mrow[j0 + q];
               }
             }
-            S[o] = acc;
+            tmem_wait_st();
           }
-          __syncthreads();
-          for (int e = tid; e < nnzP; e += T) S[(size_t)a.prow[e] * n + a.pcol[e]] += Ps[e];       // COO entries are unique
-          __threadfence_block();
-          __syncthreads();
-          // in-place Gauss-Jordan inversion (M is symmetric positive definite: no pivoting)
-          for (int k = 0; k < n; ++k) {
-            for (int i = tid; i < n; i += T) fcol[i] = S[(size_t)i * n + k];
-            __syncthreads();
-            const double piv = 1.0 / fcol[k];
-            for (int j = tid; j < n; j += T) S[(size_t)k * n + j] = (j == k) ? piv : S[(size_t)k * n + j] * piv;
-            __syncthreads();
-            for (int o = tid; o < n * n; o += T) {
-              const int i = o / n, j = o - i * n;
-              if (i == k) continue;
-              const double f = fcol[i];
-              S[o] = (j == k) ? -f * piv : fma(-f, S[(size_t)k * n + j], S[o]);
+          GP_MARK(1)
+          // in-place Gauss-Jordan inversion (M is symmetric positive definite: no pivoting).  rowb[k & 1] holds row k as it
+          // stands before sweep k: row 0 is published here, row k+1 by its owner during sweep k.
+          for (int j0 = 0; j0 < npad; j0 += 4) {
+            double v4[4];
+            if (j0 < tmd) {
+              uint32_t c8[8];
+              tmem_ld8(taddr + 2 * j0, c8);
+              tmem_wait_ld8(c8);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v4[q] = u2d(c8[2 * q], c8[2 * q + 1]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v4[q] = own ? Sx[(size_t)(j0 + q - tmd) * TS + tid] : 0.0;
             }
-            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rowb[j0 + q] = v4[q];
+            }
           }
+          for (int k = 0; k < n; ++k) {
+            double *buf = rowb + (k & 1) * npad, *nxt = rowb + ((k + 1) & 1) * npad;
+            __syncthreads();
+            if (warp == (k >> 5)) {          // scale the pivot row: buf[j] = S_kj / S_kk, buf[k] = 1 / S_kk
+              const double piv = 1.0 / buf[k];
+              __syncwarp();
+              for (int j = lid; j < npad; j += 32) buf[j] = (j == k) ? piv : buf[j] * piv;
+            }
+            const double f = row_get(k);     // S_ik before the sweep
+            __syncthreads();
+            const double piv = buf[k];
+            const bool is_k = tid == k, is_next = tid == k + 1;
+            for (int j0 = 0; j0 < npad; j0 += 4) {
+              double v4[4];
+              uint32_t c8[8];
+              if (j0 < tmd) {
+                tmem_ld8(taddr + 2 * j0, c8);
+                tmem_wait_ld8(c8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v4[q] = u2d(c8[2 * q], c8[2 * q + 1]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v4[q] = own ? Sx[(size_t)(j0 + q - tmd) * TS + tid] : 0.0;
+              }
+              const double2 b01 = *reinterpret_cast<const double2 *>(buf + j0), b23 = *reinterpret_cast<const double2 *>(buf + j0 + 2);
+              const double bq[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const double upd = (j0 + q == k) ? -f * piv : fma(-f, bq[q], v4[q]);
+                v4[q] = is_k ? bq[q] : upd;
+              }
+              if (j0 < tmd) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  c8[2 * q] = (uint32_t)__double2loint(v4[q]);
+                  c8[2 * q + 1] = (uint32_t)__double2hiint(v4[q]);
+                }
+                tmem_st8(taddr + 2 * j0, c8);
+              } else if (own) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Sx[(size_t)(j0 + q - tmd) * TS + tid] = v4[q];
+              }
+              if (is_next) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) nxt[j0 + q] = v4[q];
+              }
+            }
+            tmem_wait_st();
+          }
+          __syncthreads();
           need_op = false;
           ++my_rebuilds;
+          GP_MARK(2)
         }
         for (int i = tid; i < m; i += T) v[i] = rv[i] * z[i] - y[i];
         __syncthreads();
         for (int it = 0; it < a.check_every; ++it) {
           for (int j = tid; j < n; j += T) rb[j] = a.sigma * x[j] - qs[j] + ATcol(j, v);
           __syncthreads();
-          for (int j = tid; j < n; j += T) {
-            double acc = 0.0;
-            for (int k = 0; k < n; ++k) acc = fma(S[(size_t)k * n + j], rb[k], acc);   // S symmetric: column read is coalesced
-            xt[j] = acc;
+          {                                  // x~ = S r: a thread's own row, tensor-memory part two chunks in flight
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int j0 = 0; j0 < tmd; j0 += 8) {
+              uint32_t ca[8], cb[8];
+              tmem_ld8(taddr + 2 * j0, ca);
+              const bool two = j0 + 4 < tmd;
+              if (two) tmem_ld8(taddr + 2 * j0 + 8, cb);
+              else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cb[q] = 0u;
+              }
+              tmem_wait_ld8x2(ca, cb);
+              const double2 r01 = *reinterpret_cast<const double2 *>(rb + j0), r23 = *reinterpret_cast<const double2 *>(rb + j0 + 2);
+              a0 = fma(u2d(ca[0], ca[1]), r01.x, a0);
+              a1 = fma(u2d(ca[2], ca[3]), r01.y, a1);
+              a2 = fma(u2d(ca[4], ca[5]), r23.x, a2);
+              a3 = fma(u2d(ca[6], ca[7]), r23.y, a3);
+              if (two) {
+                const double2 r45 = *reinterpret_cast<const double2 *>(rb + j0 + 4), r67 = *reinterpret_cast<const double2 *>(rb + j0 + 6);
+                a0 = fma(u2d(cb[0], cb[1]), r45.x, a0);
+                a1 = fma(u2d(cb[2], cb[3]), r45.y, a1);
+                a2 = fma(u2d(cb[4], cb[5]), r67.x, a2);
+                a3 = fma(u2d(cb[6], cb[7]), r67.y, a3);
+              }
+            }
+            if (own) {
+              for (int j = tmd; j < npad; j += 4) {
+                const double *sx = Sx + (size_t)(j - tmd) * TS + tid;
+                a0 = fma(sx[0], rb[j], a0);
+                a1 = fma(sx[TS], rb[j + 1], a1);
+                a2 = fma(sx[2 * TS], rb[j + 2], a2);
+                a3 = fma(sx[3 * TS], rb[j + 3], a3);
+              }
+              xt[tid] = (a0 + a1) + (a2 + a3);
+            }
           }
           __syncthreads();
           for (int j = tid; j < n; j += T) x[j] = a.alpha * xt[j] + (1.0 - a.alpha) * x[j];
@@ -362,6 +503,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         }
         iter += a.check_every;
         my_iters += (unsigned long long)a.check_every;
+        GP_MARK(3)
         // ---- update_info / check_termination / adapt_rho (same arithmetic as team.cuh)
         for (int i = tid; i < m; i += T) v[i] = y[i];
         __syncthreads();
@@ -433,6 +575,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         __syncthreads();
       }
 
+      GP_MARK(4)
       // ================= rest of the control step (thread 0; trajectorySimulate.py:298-356) =================
       if (tid == 0) {
         const SimConst &c = a.sc;
@@ -589,6 +732,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         }
       }
       __syncthreads();
+      GP_MARK(5)
     }
 
     // ---------------- lane done
@@ -628,6 +772,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
       }
     }
   }
+  GP_FLUSH
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(512));
   if (tid == 0) {
     if (my_iters) atomicAdd(&a.tot[0], my_iters);
     if (my_rebuilds) atomicAdd(&a.tot[2], my_rebuilds);

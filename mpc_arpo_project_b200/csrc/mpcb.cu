@@ -137,7 +137,6 @@ struct mpcb_handle {
   bool generic_ok = false;
   GenArgs gproto;
   std::vector<void *> gen_bufs;
-  double *gen_scratch = nullptr;
   int gen_grid = 0;
   size_t gen_smem = 0;
   // batch state
@@ -457,6 +456,22 @@ static int build_team_tables(mpcb_handle *h) {
   hd.off_Ac = take(2 * Ac.size()); hd.off_ATc = take(2 * ATc.size()); hd.off_ATc2 = take(2 * ATc2.size()); hd.off_Pc = take(2 * Pc.size());
   hd.off_rowmap = take(2 * rmap.size()); hd.off_colmap = take(2 * cmap.size());
   hd.off_flags = take(m);
+  {   // shape of the rows OSQP may re-type (team.cuh tm_retype_operator): +-1 on the stage's two velocities, at most one more entry
+    hd.r3ok = (p.Nb + 1 <= 8) ? 1 : 0;
+    for (int k = 0; k < 8; ++k) { hd.r3c[k] = -1; hd.r3v[k] = 0.0; }
+    for (int k = 0; k <= p.Nb && hd.r3ok; ++k) {
+      const int r = 4 * (p.Nx + 1) + 5 * k + 3;
+      int extra = 0;
+      for (int j = 0; j < n; ++j) {
+        const double v = hp.A_s[(size_t)r * n + j];
+        if (v == 0.0 || j == 4 * k + 2 || j == 4 * k + 3) continue;
+        hd.r3c[k] = j;
+        hd.r3v[k] = v;
+        ++extra;
+      }
+      if (extra > 1 || hp.A_s[(size_t)r * n + 4 * k + 2] == 0.0 || hp.A_s[(size_t)r * n + 4 * k + 3] == 0.0) hd.r3ok = 0;
+    }
+  }
   hd.off_patch = take(16 * patch.size());
   hd.n_patch = (int)patch.size();
   hd.total = off;
@@ -960,12 +975,14 @@ static int build_generic_tables(mpcb_handle *h) {
   memcpy(g.Kd, p.K_dead, sizeof g.Kd);
   memcpy(g.Kid, p.Ki_dead, sizeof g.Kid);
   auto ev = [](int c) { return (size_t)((c + 1) & ~1); };
-  h->gen_smem = 8 * (7 * ev(n) + 10 * ev(m) + ev(nnz) + ev(g.nnzP) + ev(16 * (GEN_THREADS / 32)) + ev(n) + ev((m + 1) / 2 + 1)) +
-                sizeof(GenLane) + 64;
-  if (h->gen_smem > 220 * 1024) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path");
+  // + the operator's shared-memory part (generic.cuh): two pivot-row buffers and the row entries beyond GEN_TMD
+  const int npad = (n + 3) & ~3, tmd = std::min(npad, GEN_TMD), TS = (n + 31) & ~31;
+  h->gen_smem = 8 * (7 * ev(n) + 10 * ev(m) + ev(nnz) + ev(g.nnzP) + ev(16 * (GEN_THREADS / 32)) + ev(n) + ev((m + 1) / 2 + 1) +
+                     ev(2 * npad) + ev((npad - tmd) * TS) + 8) + sizeof(GenLane) + 64;
+  if (n > GEN_THREADS) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path (one thread per row of the operator)");
+  if (h->gen_smem > 227 * 1024) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path");
   CK(cudaFuncSetAttribute((const void *)generic_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gen_smem));
-  h->gen_grid = h->num_sms;
-  CK(cudaMalloc(&h->gen_scratch, (size_t)h->gen_grid * n * n * 8));
+  h->gen_grid = h->num_sms;              // one CTA per SM: it owns the SM's tensor memory
   h->generic_ok = true;
   return MPCB_OK;
 }
@@ -973,7 +990,6 @@ static int build_generic_tables(mpcb_handle *h) {
 static int launch_generic(mpcb_handle *h, GenArgs &g) {
   g.B = (int)h->B;
   g.xs = h->xs; g.zs = h->zs; g.ys = h->ys; g.rho = h->rho; g.u0 = h->u0; g.iter = h->iter; g.status = h->status;
-  g.scratch = h->gen_scratch;
   g.queue = h->d_queue;
   g.tot = h->d_tot;
   g.stats = h->d_stats;
@@ -1130,7 +1146,6 @@ extern "C" int mpcb_destroy(mpcb_handle *h) {
     cudaFree(h->d_V[v]);
   }
   cudaFree(h->d_tot);
-  cudaFree(h->gen_scratch);
   for (int v = 0; v < 4; ++v) cudaFree(h->d_tile_blob[v]);
   for (int v = 0; v < 4; ++v) cudaFree(h->d_wave_blob[v]);
   for (void *q : h->gen_bufs) cudaFree(q);
@@ -1444,6 +1459,12 @@ static int pull_totals(mpcb_handle *h) {
   unsigned long long t[16];
   CK(cudaMemcpyAsync(t, h->d_tot, sizeof t, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+#ifdef GEN_PROFILE
+  if (t[10]) fprintf(stderr, "[generic profile] share of CTA time: values+scaling %.1f %% | assembly %.1f %% | inversion %.1f %% | iterations %.1f %% | "
+                     "checks %.1f %% | rest of step %.1f %%   (%.2f Mcycles per solve, %.1f rebuilds per solve)\n", 100.0 * t[4] / t[10],
+                     100.0 * t[5] / t[10], 100.0 * t[6] / t[10], 100.0 * t[7] / t[10], 100.0 * t[8] / t[10], 100.0 * t[9] / t[10],
+                     t[1] ? (double)t[10] / t[1] / 1e6 : 0.0, t[1] ? (double)t[2] / t[1] : 0.0);
+#endif
 #ifdef TEAM_PROFILE
   fprintf(stderr, "[team profile] Mcycles: iterations %.1f checks %.1f rebuilds %.1f post %.1f setup %.1f | team total %.1f\n",
           t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6, t[8] / 1e6, t[9] / 1e6);

@@ -81,6 +81,9 @@ struct TeamHdr {
   int off_patch;                                                 // int4 {offA, offAT, which, 0} per signed entry
   int n_patch;
   int wA[16], wAT2[16];                                          // per-warp ELL widths
+  int r3c[8];                                                    // velocity-bound row of stage k: column of its third entry (the slack; -1: none)
+  double r3v[8];                                                 //   and that entry's scaled value (sign-variant independent); tm_retype_operator
+  int r3ok;                                                      // 0: rows do not have the expected shape -> re-typing is only counted
   int total;                                                     // bytes, multiple of 16
 };
 
@@ -581,6 +584,14 @@ __device__ __forceinline__ void tmem_wait_ld8x2(uint32_t (&r)[8], uint32_t (&q)[
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(q[0]), "+r"(q[1]),
                  "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]) :: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
@@ -652,6 +663,61 @@ __device__ __noinline__ void tm_store_operator(uint32_t taddr, double2 *dst) {
   }
 }
 
+// Row re-typing (OSQP auxil.c update_rho_vec; reference src/trajectorySimulate.py:342 -> prob.update(l, u)): when the scaled
+// bounds of a row come within RHO_TOL of each other OSQP re-classifies it as an equality, rho_vec[i] becomes 1e3 rho and the
+// KKT matrix is refactored.  Only the velocity 1-norm rows of the LOS blocks (row nX + 5k + 3, k <= Nb: upper bound
+// |p^ - r|_1) can do that, once a lane parks within centimetres of the target.  Such a row a has +-E_r D_c at the two
+// velocity columns of stage k and (k < Nc) the soft-constraint entry at the stage's slack column, so M(rho) gains
+// (1e3 - 1) rho a a' per re-typed row and the operator in tensor memory is corrected by one Sherman-Morrison step per
+// row:  S <- S - (S a)(S a)' / (1 / ((1e3 - 1) rho) + a' S a).
+// Every thread of the team calls this (it synchronises); wbuf is an N-vector scratch in shared memory (padding zero).
+template <int HALF, int NCT>
+__device__ __noinline__ void tm_retype_operator(uint32_t taddr, double *wbuf, const double *Ev, const double *Dv, int nX,
+                                                unsigned mask, int variant, double rho, int tid, int col, bool has_col,
+                                                const int *r3c, const double *r3v) {
+  const int half = tid & 1;
+  const bool col_warp = tid < NCT;
+  const double delta_inv = 1.0 / ((MPCB_RHO_EQ - 1.0) * rho);
+  for (int k = 0; (mask >> k) != 0u; ++k) {
+    if (!((mask >> k) & 1u)) continue;
+    const int r = nX + 5 * k + 3, cA = 4 * k + 2;
+    const double al = ((variant & 1) ? -1.0 : 1.0) * Ev[r] * Dv[cA], be = ((variant & 2) ? -1.0 : 1.0) * Ev[r] * Dv[cA + 1];
+    const int hA = cA / HALF, off = cA - hA * HALF;          // cA is even and HALF is even: both columns sit in one half, 4-column aligned
+    const int cS = r3c[k];
+    const double ga = cS >= 0 ? r3v[k] : 0.0;
+    const int hS = cS >= 0 ? cS / HALF : 0, offS = cS >= 0 ? cS - hS * HALF : 0;
+    double w = 0.0;
+    if (col_warp) {                                            // w = S a: entries cA, cA + 1, cS of every row
+      uint32_t c4[4];
+      tmem_ld4(taddr + 2 * off, c4);
+      tmem_wait_ld4(c4);
+      if (half == hA) w = al * u2d(c4[0], c4[1]) + be * u2d(c4[2], c4[3]);
+      tmem_ld4(taddr + 2 * (offS & ~1), c4);
+      tmem_wait_ld4(c4);
+      if (half == hS) w = fma(ga, (offS & 1) ? u2d(c4[2], c4[3]) : u2d(c4[0], c4[1]), w);
+      w += __shfl_xor_sync(0xffffffffu, w, 1);
+      if (has_col && half == 0) wbuf[col] = w;
+    }
+    __syncthreads();
+    const double f = -w / (delta_inv + al * wbuf[cA] + be * wbuf[cA + 1] + (cS >= 0 ? ga * wbuf[cS] : 0.0));
+    if (col_warp) {
+      const double *wc = wbuf + half * HALF;
+#pragma unroll 1
+      for (int c = 0; c < HALF; c += 2) {
+        uint32_t c4[4];
+        tmem_ld4(taddr + 2 * c, c4);
+        tmem_wait_ld4(c4);
+        const double s0 = fma(f, wc[c], u2d(c4[0], c4[1])), s1 = fma(f, wc[c + 1], u2d(c4[2], c4[3]));
+        const uint32_t w4[4] = {(uint32_t)__double2loint(s0), (uint32_t)__double2hiint(s0), (uint32_t)__double2loint(s1),
+                                (uint32_t)__double2hiint(s1)};
+        tmem_st4(taddr + 2 * c, w4);
+      }
+      tmem_wait_st();
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // N variables, M rows (M <= 256, 2N <= 256); WA (<= 8), WAT2 (<= 8, entry PAIRS), WP are the maximum
 // ELL widths the instantiation supports.  Of the HALF entries of S a thread owns, the last SS live in
@@ -696,6 +762,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
   UkfScratch &ukf = *reinterpret_cast<UkfScratch *>(Ssm + SS * NCT);
   LaneCtx &L = *reinterpret_cast<LaneCtx *>(reinterpret_cast<unsigned char *>(&ukf) + ((sizeof(UkfScratch) + 15) & ~15));
   __shared__ int s_lane;
+  __shared__ unsigned s_eqmask;
 
   for (int o = tid * 16; o < h.total; o += TEAM * 16)
     *reinterpret_cast<int4 *>(smem + o) = *reinterpret_cast<const int4 *>(a.blob + o);
@@ -847,6 +914,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
   int op_variant = 0;                    // sign variant baked into Avals / ATvals (blob = variant 0)
   double op_rho = -1.0;                  // (rho, variant) the operator S currently held was built for: S depends on nothing
   int s_variant = -1;                    // else, so it survives from one lane to the next when both match
+  unsigned op_mask = 0u;                 // re-typed rows folded into S (tm_retype_operator); the operator caches hold mask-0 operators only
   constexpr int SCHUNKS = HALF / 2;      // double2 chunks of S per thread (operator cache layout [chunk][thread])
   auto s_load = [&](const double2 *src) { if constexpr (TM) tm_load_operator<HALF, NCT>(taddr, src); };     // col_warp threads,
   auto s_store = [&](double2 *dst) { if constexpr (TM) tm_store_operator<HALF, NCT>(taddr, dst); };         // pointer offset by tid
@@ -900,6 +968,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
       if (col_warp) s_load(reinterpret_cast<const double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid);
       op_rho = L.rho;
       s_variant = L.variant;
+      op_mask = 0u;
     }
     TP_MARK(4)
 
@@ -907,16 +976,26 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
     while (!L.fin) {
       const int variant = L.variant;
       double rho = L.rho;
+      int r3k = -1;                      // >= 0: this thread's row is the velocity-bound row of stage r3k
       if (has_row) {
         double lo = lt[row], hi = ut[row];
         if (row < 4) lo = hi = -L.par[row] * Ev[row];
         else if (row >= M - 2) lo = hi = L.par[5 + (row - (M - 2))] * Ev[row];
         else if (row >= a.nX && row < a.nX + 5 * (a.Nb + 1) && (row - a.nX) % 5 == 3) {
           hi = L.par[4] * Ev[row];
-          if (hi - lo < MPCB_RHO_TOL) L.flip = 1;      // benign race: every writer stores 1
+          r3k = (row - a.nX) / 5;
         }
         lobuf[tid] = lo;                               // own slot only: no barrier needed before own reads
         hibuf[tid] = hi;
+      }
+      if (tid == 0) {                                  // rows OSQP treats as equalities at this step (tm_retype_operator)
+        unsigned mk = 0u;
+        for (int k = 0; k <= a.Nb && k < 32; ++k) {
+          const int r = a.nX + 5 * k + 3;
+          if (L.par[4] * Ev[r] - lt[r] < MPCB_RHO_TOL) mk |= 1u << k;
+        }
+        if (mk) L.flip = 1;
+        s_eqmask = mk;
       }
       if (variant != op_variant) {       // re-sign the (Nx+1) velocity rows of A and A'
         for (int p = tid; p < h.n_patch; p += TEAM) {
@@ -933,10 +1012,12 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
       first_solve = false;
       int visit_left = a.visit_iters;
       const bool resigned = variant != op_variant;
-      bool need_op = (variant != s_variant) || (rho != op_rho);
       op_variant = variant;
-      const uint8_t fl = has_row ? flags[row] : (uint8_t)8;
       __syncthreads();
+      const unsigned eqmask = (TM && h.r3ok) ? s_eqmask : 0u;      // register-resident operator (MPCB_TEAM=regs): re-typing is only counted
+      bool need_op = (variant != s_variant) || (rho != op_rho) || (eqmask != op_mask);
+      uint8_t fl = has_row ? flags[row] : (uint8_t)8;
+      if (r3k >= 0 && ((eqmask >> r3k) & 1u)) fl |= 4;  // re-typed row: rho_vec = 1e3 rho
       if (TM && resigned) load_tables();
 
       // =============================== one solve ===============================
@@ -946,7 +1027,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
           // A sign-variant flip at unchanged rho tends to flip back (95 % of config 4's rebuilds): park the OUTGOING
           // operator before it is overwritten, unless the cache has it already.  Operators replaced because rho adapted are
           // not parked (they rarely return, and config 2 would pay a 64 KB store per rebuild for a 5 % hit rate).
-          if (op_rho == rho && s_variant != variant && s_variant >= 0) {
+          if (op_rho == rho && s_variant != variant && s_variant >= 0 && op_mask == 0u) {
             bool have = false;
 #pragma unroll
             for (int q = 0; q < TEAM_OPC; ++q) have = have || (s_oc_rho[q] == op_rho && s_oc_var[q] == s_variant);
@@ -972,6 +1053,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
             s_load(reinterpret_cast<const double2 *>(a.ocache) + ((size_t)blockIdx.x * TEAM_OPC + oc_hit) * (SCHUNKS * NCT) + tid);
           op_rho = rho;
           s_variant = variant;
+          op_mask = 0u;
           need_op = false;
         }
         if (need_op) {                   // S = V diag(1/(1+rho*lam)) V'
@@ -1058,9 +1140,17 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
           }
           op_rho = rho;
           s_variant = variant;
+          op_mask = 0u;
           need_op = false;
           ++my_rebuilds;
           TP_MARK(2)
+        }
+        if constexpr (TM) {
+          if (op_mask != eqmask) {       // (team-uniform) fold the re-typed rows into the fresh S(rho)
+            __syncthreads();
+            tm_retype_operator<HALF, NCT>(taddr, xtbuf, Ev, Dv, a.nX, eqmask, variant, rho, tid, col, has_col, h.r3c, h.r3v);
+            op_mask = eqmask;
+          }
         }
         const double rv = (fl & 8) ? MPCB_RHO_MIN : ((fl & 4) ? MPCB_RHO_EQ * rho : rho);
         if (has_row) {
@@ -1307,7 +1397,7 @@ __global__ void __launch_bounds__(TT, CT) team_kernel(const __grid_constant__ Te
 
     // ---- list mode: leave the operator in the lane's cache slot unless the slot already holds it
     if constexpr (TM) {
-      const bool put = a.list && a.scache && op_rho >= 0.0 && (L.c_rho != op_rho || L.c_var != s_variant);
+      const bool put = a.list && a.scache && op_rho >= 0.0 && op_mask == 0u && (L.c_rho != op_rho || L.c_var != s_variant);
       __syncthreads();
       if (put) {
         if (col_warp) s_store(reinterpret_cast<double2 *>(a.scache) + (size_t)ln * (SCHUNKS * NCT) + tid);

@@ -50,14 +50,14 @@ def test_batched_form_equals_scalar_oracle(name):
         np.testing.assert_allclose(out['x_est'][:T + 1, b].T, r.x_est[:, :T + 1], rtol=1e-7, atol=1e-6)
 
 
-def retype_lanes(B=12, seed=5, nsim=40, sigma=0.002):
+def retype_lanes(B=12, seed=5, nsim=40, sigma=0.002, Nx=10):
     """Lanes that start within centimetres of the target: the velocity 1-norm bound ``|p^ - r|_1`` of the LOS rows then
     comes within RHO_TOL of its lower bound and OSQP re-types those rows as equalities."""
     rng = np.random.default_rng(seed)
     x0 = np.array([2.5, 0., 0, 0])[None, :] + np.concatenate(
         [rng.uniform(0.03, 0.4, (B, 1)), rng.uniform(-0.02, 0.02, (B, 1)), np.zeros((B, 2))], axis=1)
     noise = sigma * rng.standard_normal((nsim // 5 + 1, 2, B))
-    return dict(Nx=10, sigma=sigma, noise_length=5, T_final=nsim * 0.5), x0, noise
+    return dict(Nx=Nx, sigma=sigma, noise_length=5, T_final=nsim * 0.5), x0, noise
 
 
 def test_row_retyping_matches_the_kkt_oracle():

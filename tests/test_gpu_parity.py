@@ -513,6 +513,30 @@ def test_operator_cache_does_not_change_results(monkeypatch):
     assert np.array_equal(a.x_true, b.x_true, equal_nan=True) and np.array_equal(a.ctrl_hist, b.ctrl_hist, equal_nan=True)
 
 
+@pytest.mark.parametrize("Nx,B", [(10, 48), (20, 24), (30, 16)])
+def test_row_retyping_on_the_team_kernel(Nx, B):
+    """lanes parked next to the target make OSQP re-type the velocity-bound rows as equalities
+    (rho_vec = 1e3 rho + refactor).  The team kernel folds the re-typed rows into its tensor-memory operator with one
+    Sherman-Morrison step per row; iteration counts, statuses and controls must follow the oracle that models the
+    re-typing (checked against the scalar KKT oracle in tests/test_batched_ref.py) -- and differ from the one that does not."""
+    from test_batched_ref import retype_lanes
+    case, x0, noise = retype_lanes(B=B, seed=11, Nx=Nx)
+    sc, mp, fp, _ = make_params(M, case)
+    got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
+    ref = simulate_discrete_batch(sc, mp, fp, x0, noise, chol_fail='clamp')
+    off = simulate_discrete_batch(sc, mp, fp, x0, noise, chol_fail='clamp', retype=False)
+    # (the oracle also flags a lane whose LAST parameter refresh -- after its final solve -- would re-type a row)
+    assert B // 3 <= int(got.stats["flip_lanes"]) <= int(ref["flip_flag"].sum())
+    assert np.array_equal(got.i_term, ref['i_term']) and np.array_equal(got.iters.astype(int), ref['iters'])
+    assert np.array_equal(got.status.astype(int), ref['status']) and np.array_equal(got.ctrlr_seq, ref['ctrlr_seq'])
+    for b in range(B):      # re-typed solves carry rho_vec = 1e3 rho on rows scaled by E ~ 1e-3: 1e-5 here (task bar 1e-4), measured 1.2e-6
+        T = int(ref['i_term'][b])
+        np.testing.assert_allclose(got.ctrl_hist[:, :T + 1, b].T, ref['ctrl_hist'][:T + 1, b], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(got.x_true[:, :T + 1, b].T, ref['x_true'][:T + 1, b], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(got.x_est[:, :T + 1, b].T, ref['x_est'][:T + 1, b], rtol=0, atol=1e-5)
+    assert not np.array_equal(off["iters"], ref["iters"]), "the scenario no longer exercises re-typing"
+
+
 # ------------------------------------------------------------------------------------ Monte-Carlo drivers
 def test_monte_carlo_reductions_match_per_lane_results():
     """disturbRejComp / success_rates_test as batched calls: the device-side statistics equal what the

@@ -63,3 +63,17 @@ def test_debris_problem_carries_unscaled_data_and_deadbeat_gains():
     nX = 4 * (p.Nx + 1)
     assert len(diff) == p.Nx + 1 and all(r == nX + 5 * k + 4 and c == 4 * k for k, (r, c) in enumerate(diff))
     np.testing.assert_allclose(p.debris_verts, debris.constructVertArr())
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"Nx{c['Nx']}{'_it' if c.get('inTrack') else ''}")
+def test_dual_infeasibility_certificate_cannot_fire(case):
+    """OSQP's ``check_termination`` also tests a dual-infeasibility certificate (``is_dual_infeasible``, restated in
+    oracle/osqp_ref.py): ``q'dx < -eps |dx|`` with ``|P dx| < eps |dx|`` (eps_dual_inf = 1e-4, norms unscaled).  The kernels do not
+    carry it (they would need x of the previous iteration), and need not: every problem family of this path has P > 0 --
+    state, input, slack AND disturbance variables are all weighted -- so ``|P dx|_inf >= lambda_min |dx|_inf / sqrt(n)``,
+    three orders of magnitude above the threshold.  A status of DUAL_INFEASIBLE is unreachable for the reference as well."""
+    sc, mp, fp, _ = make_params(M, case)
+    p = M.build_problem(sc, mp, fp, None)
+    P = np.asarray(p.P)
+    lam_min = np.linalg.eigvalsh(0.5 * (P + P.T)).min()
+    assert lam_min / np.sqrt(P.shape[0]) > 100 * 1e-4, lam_min
