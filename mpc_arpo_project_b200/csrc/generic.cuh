@@ -44,6 +44,7 @@ struct GenArgs {
   const int *rowptr, *colidx, *colptr, *rowidx, *cscpos;
   const double *baseA;        // [nnzA]
   const unsigned char *kindA; // 0 constant, 1 carries sign(vx_hat), 2 sign(vy_hat), 3 carries -slope
+  int nlong, longcols[8];     // columns of A with more than 32 entries (the disturbance variables touch every dynamics row): a warp each in A'v
   const int *prow, *pcol;     // P in COO (both triangles), row-major
   const int *prowptr;         // [n+1] first COO entry of every row
   const double *pval, *q_u, *l_u, *u_u;
@@ -134,6 +135,18 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
   const int npad = (n + 3) & ~3, tmd = npad < GEN_TMD ? npad : GEN_TMD, TS = (n + 31) & ~31;
   double *rowb = take(2 * npad), *Sx = take((npad - tmd) * TS);
   GenLane &L = *reinterpret_cast<GenLane *>(p);
+  // sparsity pattern of A in shared memory (uint16: m, n, nnz < 65536): the per-iteration products walk these lists, and from
+  // global memory every walk is a chain of dependent L1 / L2 round trips
+  uint16_t *ixp = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(p) + ((sizeof(GenLane) + 15) & ~(size_t)15));
+  uint16_t *ix_rowptr = ixp, *ix_colptr = ix_rowptr + ((m + 2) & ~1), *ix_colidx = ix_colptr + ((n + 2) & ~1),
+           *ix_rowidx = ix_colidx + ((nnzA + 1) & ~1), *ix_cscpos = ix_rowidx + ((nnzA + 1) & ~1);
+  for (int i = tid; i <= m; i += T) ix_rowptr[i] = (uint16_t)a.rowptr[i];
+  for (int j = tid; j <= n; j += T) ix_colptr[j] = (uint16_t)a.colptr[j];
+  for (int e = tid; e < nnzA; e += T) {
+    ix_colidx[e] = (uint16_t)a.colidx[e];
+    ix_rowidx[e] = (uint16_t)a.rowidx[e];
+    ix_cscpos[e] = (uint16_t)a.cscpos[e];
+  }
   __shared__ int s_lane;
   __shared__ double s_c;
   __shared__ uint32_t s_tmem;
@@ -180,12 +193,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
   };
   auto Arow = [&](int i, const double *vec) -> double {        // (A_s vec)[i]
     double acc = 0.0;
-    for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) acc = fma(As[e], vec[a.colidx[e]], acc);
+    for (int e = ix_rowptr[i]; e < ix_rowptr[i + 1]; ++e) acc = fma(As[e], vec[ix_colidx[e]], acc);
     return acc;
   };
   auto ATcol = [&](int j, const double *vec) -> double {       // (A_s' vec)[j]
     double acc = 0.0;
-    for (int e = a.colptr[j]; e < a.colptr[j + 1]; ++e) acc = fma(As[a.cscpos[e]], vec[a.rowidx[e]], acc);
+    for (int e = ix_colptr[j]; e < ix_colptr[j + 1]; ++e) acc = fma(As[ix_cscpos[e]], vec[ix_rowidx[e]], acc);
     return acc;
   };
 
@@ -266,10 +279,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           atomicMax(reinterpret_cast<unsigned long long *>(&cmax[a.pcol[e]]), (unsigned long long)__double_as_longlong(fabs(Ps[e])));
         for (int i = tid; i < m; i += T) {
           double rm = 0.0;
-          for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) {
+          for (int e = ix_rowptr[i]; e < ix_rowptr[i + 1]; ++e) {
             const double av = fabs(As[e]);
             rm = fmax(rm, av);
-            atomicMax(reinterpret_cast<unsigned long long *>(&cmax[a.colidx[e]]), (unsigned long long)__double_as_longlong(av));
+            atomicMax(reinterpret_cast<unsigned long long *>(&cmax[ix_colidx[e]]), (unsigned long long)__double_as_longlong(av));
           }
           rmax[i] = rm;
         }
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         __syncthreads();
         for (int e = tid; e < nnzP; e += T) Ps[e] = cmax[a.prow[e]] * Ps[e] * cmax[a.pcol[e]];
         for (int i = tid; i < m; i += T) {
-          for (int e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) As[e] = rmax[i] * As[e] * cmax[a.colidx[e]];
+          for (int e = ix_rowptr[i]; e < ix_rowptr[i + 1]; ++e) As[e] = rmax[i] * As[e] * cmax[ix_colidx[e]];
           E[i] *= rmax[i];
         }
         for (int j = tid; j < n; j += T) { qs[j] *= cmax[j]; D[j] *= cmax[j]; }
@@ -348,11 +361,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
             for (int j = 0; j < npad; ++j) Mrow[j] = 0.0;
             if (own) {
               Mrow[tid] = a.sigma;
-              for (int ea = a.colptr[tid]; ea < a.colptr[tid + 1]; ++ea) {
-                const int r = a.rowidx[ea];
-                const double w = rv[r] * As[a.cscpos[ea]];
-                for (int e = a.rowptr[r]; e < a.rowptr[r + 1]; ++e) {
-                  const int j = a.colidx[e];
+              for (int ea = ix_colptr[tid]; ea < ix_colptr[tid + 1]; ++ea) {
+                const int r = ix_rowidx[ea];
+                const double w = rv[r] * As[ix_cscpos[ea]];
+                for (int e = ix_rowptr[r]; e < ix_rowptr[r + 1]; ++e) {
+                  const int j = ix_colidx[e];
                   Mrow[j] = fma(w, As[e], Mrow[j]);
                 }
               }
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           }
           GP_MARK(1)
           // in-place Gauss-Jordan inversion (M is symmetric positive definite: no pivoting).  rowb[k & 1] holds row k as it
-          // stands before sweep k: row 0 is published here, row k+1 by its owner during sweep k.
+          // stands before sweep k (unscaled): row 0 is published here, row k+1 by its owner during sweep k.
           for (int j0 = 0; j0 < npad; j0 += 4) {
             double v4[4];
             if (j0 < tmd) {
@@ -395,48 +408,77 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
           for (int k = 0; k < n; ++k) {
             double *buf = rowb + (k & 1) * npad, *nxt = rowb + ((k + 1) & 1) * npad;
             __syncthreads();
-            if (warp == (k >> 5)) {          // scale the pivot row: buf[j] = S_kj / S_kk, buf[k] = 1 / S_kk
-              const double piv = 1.0 / buf[k];
-              __syncwarp();
-              for (int j = lid; j < npad; j += 32) buf[j] = (j == k) ? piv : buf[j] * piv;
-            }
-            const double f = row_get(k);     // S_ik before the sweep
-            __syncthreads();
-            const double piv = buf[k];
+            // every thread scales on the fly (no separate pass over the pivot row, one barrier per sweep):
+            //   row k   <- S_kj / S_kk, S_kk <- 1 / S_kk;      row i <- S_ij - (S_ik / S_kk) S_kj, S_ik <- -S_ik / S_kk
+            const double piv = 1.0 / buf[k];
+            const double g = row_get(k) * piv;                   // S_ik / S_kk
             const bool is_k = tid == k, is_next = tid == k + 1;
-            for (int j0 = 0; j0 < npad; j0 += 4) {
-              double v4[4];
-              uint32_t c8[8];
-              if (j0 < tmd) {
-                tmem_ld8(taddr + 2 * j0, c8);
-                tmem_wait_ld8(c8);
+            const double mul = is_k ? piv : -g, diag = is_k ? piv : -g;
+            auto upd = [&](int j, double b, double old) -> double {        // one FMA per entry for owner and non-owner alike
+              return (j == k) ? diag : fma(mul, b, is_k ? 0.0 : old);
+            };
+            const double2 *buf2 = reinterpret_cast<const double2 *>(buf);
+            double2 *nxt2 = reinterpret_cast<double2 *>(nxt);
+            int j0 = 0;
+            // tensor-memory part, 32 entries per step: four 16-column loads in flight, one wait, four stores
+            for (; j0 + 32 <= tmd; j0 += 32) {
+              uint32_t q[4][16];
+              tmem_ld16(taddr + 2 * j0, q[0]);
+              tmem_ld16(taddr + 2 * j0 + 16, q[1]);
+              tmem_ld16(taddr + 2 * j0 + 32, q[2]);
+              tmem_ld16(taddr + 2 * j0 + 48, q[3]);
+              double2 b2[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v4[q] = u2d(c8[2 * q], c8[2 * q + 1]);
-              } else {
+              for (int i = 0; i < 16; ++i) b2[i] = buf2[j0 / 2 + i];
+              tmem_wait_ld2(q[0], q[1]);
+              tmem_wait_ld2(q[2], q[3]);
+              double2 r2[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v4[q] = own ? Sx[(size_t)(j0 + q - tmd) * TS + tid] : 0.0;
+              for (int i = 0; i < 16; ++i) {
+                const int g = i >> 2, e = (i & 3) * 4;           // entries 2i, 2i+1 of the group = registers e..e+3 of load g
+                r2[i].x = upd(j0 + 2 * i, b2[i].x, u2d(q[g][e], q[g][e + 1]));
+                r2[i].y = upd(j0 + 2 * i + 1, b2[i].y, u2d(q[g][e + 2], q[g][e + 3]));
+                q[g][e] = (uint32_t)__double2loint(r2[i].x); q[g][e + 1] = (uint32_t)__double2hiint(r2[i].x);
+                q[g][e + 2] = (uint32_t)__double2loint(r2[i].y); q[g][e + 3] = (uint32_t)__double2hiint(r2[i].y);
               }
-              const double2 b01 = *reinterpret_cast<const double2 *>(buf + j0), b23 = *reinterpret_cast<const double2 *>(buf + j0 + 2);
-              const double bq[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const double upd = (j0 + q == k) ? -f * piv : fma(-f, bq[q], v4[q]);
-                v4[q] = is_k ? bq[q] : upd;
-              }
-              if (j0 < tmd) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  c8[2 * q] = (uint32_t)__double2loint(v4[q]);
-                  c8[2 * q + 1] = (uint32_t)__double2hiint(v4[q]);
-                }
-                tmem_st8(taddr + 2 * j0, c8);
-              } else if (own) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) Sx[(size_t)(j0 + q - tmd) * TS + tid] = v4[q];
-              }
+              tmem_st16(taddr + 2 * j0, q[0]);
+              tmem_st16(taddr + 2 * j0 + 16, q[1]);
+              tmem_st16(taddr + 2 * j0 + 32, q[2]);
+              tmem_st16(taddr + 2 * j0 + 48, q[3]);
               if (is_next) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) nxt[j0 + q] = v4[q];
+                for (int i = 0; i < 16; ++i) nxt2[j0 / 2 + i] = r2[i];
+              }
+            }
+            for (; j0 < tmd; j0 += 4) {                          // tail of the tensor-memory part
+              uint32_t c8[8];
+              tmem_ld8(taddr + 2 * j0, c8);
+              const double2 ba = buf2[j0 / 2], bb = buf2[j0 / 2 + 1];
+              tmem_wait_ld8(c8);
+              double2 ra, rb2;
+              ra.x = upd(j0, ba.x, u2d(c8[0], c8[1]));
+              ra.y = upd(j0 + 1, ba.y, u2d(c8[2], c8[3]));
+              rb2.x = upd(j0 + 2, bb.x, u2d(c8[4], c8[5]));
+              rb2.y = upd(j0 + 3, bb.y, u2d(c8[6], c8[7]));
+              c8[0] = (uint32_t)__double2loint(ra.x); c8[1] = (uint32_t)__double2hiint(ra.x);
+              c8[2] = (uint32_t)__double2loint(ra.y); c8[3] = (uint32_t)__double2hiint(ra.y);
+              c8[4] = (uint32_t)__double2loint(rb2.x); c8[5] = (uint32_t)__double2hiint(rb2.x);
+              c8[6] = (uint32_t)__double2loint(rb2.y); c8[7] = (uint32_t)__double2hiint(rb2.y);
+              tmem_st8(taddr + 2 * j0, c8);
+              if (is_next) { nxt2[j0 / 2] = ra; nxt2[j0 / 2 + 1] = rb2; }
+            }
+            if (own) {                                           // shared-memory part, four entries per step
+              for (; j0 < npad; j0 += 4) {
+                double *sx = Sx + (size_t)(j0 - tmd) * TS + tid;
+                const double2 ba = buf2[j0 / 2], bb = buf2[j0 / 2 + 1];
+                const double o0 = sx[0], o1 = sx[TS], o2 = sx[2 * TS], o3 = sx[3 * TS];
+                double2 ra, rb2;
+                ra.x = upd(j0, ba.x, o0);
+                ra.y = upd(j0 + 1, ba.y, o1);
+                rb2.x = upd(j0 + 2, bb.x, o2);
+                rb2.y = upd(j0 + 3, bb.y, o3);
+                sx[0] = ra.x; sx[TS] = ra.y; sx[2 * TS] = rb2.x; sx[3 * TS] = rb2.y;
+                if (is_next) { nxt2[j0 / 2] = ra; nxt2[j0 / 2 + 1] = rb2; }
               }
             }
             tmem_wait_st();
@@ -449,11 +491,47 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
         for (int i = tid; i < m; i += T) v[i] = rv[i] * z[i] - y[i];
         __syncthreads();
         for (int it = 0; it < a.check_every; ++it) {
-          for (int j = tid; j < n; j += T) rb[j] = a.sigma * x[j] - qs[j] + ATcol(j, v);
+          for (int j = tid; j < n; j += T)
+            if (ix_colptr[j + 1] - ix_colptr[j] <= 32) rb[j] = a.sigma * x[j] - qs[j] + ATcol(j, v);
+          for (int q = warp; q < a.nlong; q += NW) {              // long columns: 32 lanes share the entries, fixed butterfly sum
+            const int j = a.longcols[q];
+            double acc = 0.0;
+            for (int e = ix_colptr[j] + lid; e < ix_colptr[j + 1]; e += 32) acc = fma(As[ix_cscpos[e]], v[ix_rowidx[e]], acc);
+            acc = warp_sum(acc);
+            if (lid == 0) rb[j] = a.sigma * x[j] - qs[j] + acc;
+          }
           __syncthreads();
           {                                  // x~ = S r: a thread's own row, tensor-memory part two chunks in flight
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int j0 = 0; j0 < tmd; j0 += 8) {
+            int j0 = 0;
+            if (tmd >= 32) {             // 32 entries per step in two halves: the next half's loads fly while this half's FMAs issue
+              uint32_t A0[16], A1[16], B0[16], B1[16];
+              auto use16 = [&](const uint32_t (&c0)[16], const uint32_t (&c1)[16], int jb) {
+                const double2 *r2 = reinterpret_cast<const double2 *>(rb + jb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const double2 ra = r2[i], rc = r2[4 + i];
+                  a0 = fma(u2d(c0[4 * i], c0[4 * i + 1]), ra.x, a0);
+                  a1 = fma(u2d(c0[4 * i + 2], c0[4 * i + 3]), ra.y, a1);
+                  a2 = fma(u2d(c1[4 * i], c1[4 * i + 1]), rc.x, a2);
+                  a3 = fma(u2d(c1[4 * i + 2], c1[4 * i + 3]), rc.y, a3);
+                }
+              };
+              tmem_ld16(taddr, A0); tmem_ld16(taddr + 16, A1);
+              tmem_ld16(taddr + 32, B0); tmem_ld16(taddr + 48, B1);
+              tmem_wait_ld2(A0, A1);
+              tmem_wait_ld2(B0, B1);
+              for (; j0 + 32 <= tmd; j0 += 32) {
+                use16(A0, A1, j0);
+                const bool more = j0 + 64 <= tmd;
+                if (more) { tmem_ld16(taddr + 2 * (j0 + 32), A0); tmem_ld16(taddr + 2 * (j0 + 32) + 16, A1); }
+                use16(B0, B1, j0 + 16);
+                if (more) { tmem_ld16(taddr + 2 * (j0 + 48), B0); tmem_ld16(taddr + 2 * (j0 + 48) + 16, B1); }
+                tmem_wait_ld2(A0, A1);
+                tmem_wait_ld2(B0, B1);
+              }
+            }
+            for (; j0 < tmd; j0 += 8) {  // tail: eight (or the last four) entries per step
               uint32_t ca[8], cb[8];
               tmem_ld8(taddr + 2 * j0, ca);
               const bool two = j0 + 4 < tmd;

@@ -905,6 +905,7 @@ static int gen_upload(mpcb_handle *h, const std::vector<Tv> &v, const Tv **out) 
 }
 
 static int build_generic_tables(mpcb_handle *h) {
+  int g0_nlong = 0, g0_longcols[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const HostProblem &hp = h->hp;
   const mpcb_problem &p = hp.p;
   const int n = p.n, m = p.m, nX = 4 * (p.Nx + 1);
@@ -950,6 +951,12 @@ static int build_generic_tables(mpcb_handle *h) {
         pcol.push_back(c);
         pval.push_back(hp.P_u[(size_t)r * n + c]);
       }
+  g0_nlong = 0;
+  for (int c = 0; c < n; ++c)
+    if (colptr[c + 1] - colptr[c] > 32) {
+      if (g0_nlong == 8) return fail(MPCB_ERR_INVALID, "per-lane path: more than 8 columns of A with over 32 entries");
+      g0_longcols[g0_nlong++] = c;
+    }
   std::vector<int> prowptr(n + 1, 0);
   for (int r : prow) prowptr[r + 1]++;
   for (int r = 0; r < n; ++r) prowptr[r + 1] += prowptr[r];
@@ -957,6 +964,8 @@ static int build_generic_tables(mpcb_handle *h) {
   memset(&g, 0, sizeof g);
   g.n = n; g.m = m; g.nX = nX; g.Nx = p.Nx; g.Nb = p.Nb; g.Nc = p.Nc; g.uoff = nX;
   g.nnzA = nnz; g.nnzP = (int)pval.size(); g.scaling = p.scaling;
+  g.nlong = g0_nlong;
+  memcpy(g.longcols, g0_longcols, sizeof g.longcols);
   RC(gen_upload(h, rowptr, &g.rowptr)); RC(gen_upload(h, colidx, &g.colidx)); RC(gen_upload(h, colptr, &g.colptr));
   RC(gen_upload(h, rowidx, &g.rowidx)); RC(gen_upload(h, cscpos, &g.cscpos)); RC(gen_upload(h, base, &g.baseA));
   RC(gen_upload(h, kind, &g.kindA)); RC(gen_upload(h, prow, &g.prow)); RC(gen_upload(h, pcol, &g.pcol));
@@ -978,7 +987,9 @@ static int build_generic_tables(mpcb_handle *h) {
   // + the operator's shared-memory part (generic.cuh): two pivot-row buffers and the row entries beyond GEN_TMD
   const int npad = (n + 3) & ~3, tmd = std::min(npad, GEN_TMD), TS = (n + 31) & ~31;
   h->gen_smem = 8 * (7 * ev(n) + 10 * ev(m) + ev(nnz) + ev(g.nnzP) + ev(16 * (GEN_THREADS / 32)) + ev(n) + ev((m + 1) / 2 + 1) +
-                     ev(2 * npad) + ev((npad - tmd) * TS) + 8) + sizeof(GenLane) + 64;
+                     ev(2 * npad) + ev((npad - tmd) * TS) + 8) + sizeof(GenLane) + 64 +
+                2 * (size_t)(((m + 2) & ~1) + ((n + 2) & ~1) + 3 * ((nnz + 1) & ~1)) + 16;      // + the uint16 copies of the sparsity pattern
+  if (nnz > 65535 || m > 65535) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path (16-bit sparsity indices)");
   if (n > GEN_THREADS) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path (one thread per row of the operator)");
   if (h->gen_smem > 227 * 1024) return fail(MPCB_ERR_INVALID, "problem too large for the per-lane path");
   CK(cudaFuncSetAttribute((const void *)generic_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gen_smem));
@@ -1784,7 +1795,13 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     }
     long below = 10L * h->num_sms * h->team_ctas;
     if (const char *e = getenv("MPCB_RESUME_BELOW")) below = atol(e);
-    RC(run_rounds(h, aa, pa, 0, want_tile(h), !want_tile(h) && want_wave(h, true), can_resume ? &tr : nullptr, below));
+    // Solver block of the rounds.  Discrete simulator, >= wave_min_lanes: multi-RHS wave kernel, 25 iterations per round, the last
+    // lanes handed to the team kernel.  Continuous simulator: the team kernel in list mode (every round's solves run to
+    // completion, one round per control step) -- measured on config 3 (65 536 lanes): 2.43 s per step against 3.13 s with wave
+    // rounds, which pay a post_kernel pass (500 RK4 substeps per lane) and a host round trip per 25 iterations.
+    const bool forced_wave = getenv("MPCB_SOLVER") && strcmp(getenv("MPCB_SOLVER"), "wave") == 0;
+    const bool use_wave = !want_tile(h) && want_wave(h, true) && (mode == MODE_DISCRETE || forced_wave);
+    RC(run_rounds(h, aa, pa, 0, want_tile(h), use_wave, can_resume ? &tr : nullptr, below));
     finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;

@@ -23,6 +23,7 @@ def _host(a):
 
 
 RHO_DECISION_TOL = 1e-2
+RHO_SAME_TOL = 1e-6
 
 
 def full_horizon_report(got, ref, u_bar=1e-4, rho_tol=RHO_DECISION_TOL):
@@ -42,28 +43,41 @@ def full_horizon_report(got, ref, u_bar=1e-4, rho_tol=RHO_DECISION_TOL):
     differ = ((it_g != it_r) | (st_g != st_r) | (cs_g != cs_r)) & live
     rho_g = _host(getattr(got, "rho", None))
     rho_r = ref.get("rho_hist")
+    differ_strict = differ.copy()
     if rho_g is not None and rho_r is not None:
         # adaptive rho is a discrete decision too (OSQP adapts when the estimate leaves [rho/5, 5 rho]): a lane where one side
         # adapted and the other did not has diverged even while the iteration counts still coincide
         # (RHO_DECISION_TOL: an adaptation multiplies rho by >= 5 or <= 1/5, so 1 % separates "adapted differently" from the
         # 1e-9..1e-4 by which two float64 evaluations of sqrt(pri/dua) differ once the KKT system is ill-conditioned)
         with np.errstate(invalid="ignore"):
-            differ |= (np.abs(rho_g - rho_r) > rho_tol * np.abs(rho_r)) & live
+            gap = np.abs(rho_g - rho_r) / np.abs(rho_r)
+        gap = np.nan_to_num(gap, nan=0.0)
+        differ |= (gap > rho_tol) & live
+        # ... but a rho that differs in the 5th digit already makes the NEXT solve a different OSQP run (same decisions, iterates
+        # apart by a fraction of OSQP's own 1e-3 termination tolerance): controls are compared on the strict prefix, where rho
+        # agrees to RHO_SAME_TOL as well
+        differ_strict |= (gap > RHO_SAME_TOL) & live
     first = np.where(differ.any(axis=0), differ.argmax(axis=0), nsim)                               # first differing solve
+    first_s = np.where(differ_strict.any(axis=0), differ_strict.argmax(axis=0), nsim)
     # a lane also diverges where the two sides stop at different steps
     first = np.where(term_g != term_r, np.minimum(first, np.minimum(term_g, term_r)), first)
+    first_s = np.minimum(first_s, first)
     exact = (first >= nsim) & (term_g == term_r)
+    exact_s = (first_s >= nsim) & (term_g == term_r)
     # controls / states on the matching prefix: step i's command is ctrl[i+1]; it is comparable while solves 0..i matched
     upto = np.minimum(first, np.minimum(term_g, term_r))                                           # solves 0..upto-1 match
+    upto_s = np.minimum(first_s, np.minimum(term_g, term_r))
     tt = np.arange(nsim + 1)[:, None]
-    pre = tt <= upto[None, :]
+    pre = tt <= upto_s[None, :]
     du = np.where(pre[:, :, None], np.abs(u_g - u_r), 0.0)
     dx = np.where(pre[:, :, None], np.abs(x_g - x_r), 0.0)
+    du_dec = np.nan_to_num(np.where((tt <= upto[None, :])[:, :, None], np.abs(u_g - u_r), 0.0), nan=0.0)
     du = np.nan_to_num(du, nan=0.0)
     dx = np.nan_to_num(dx, nan=0.0)
     rep = {
         "lanes": int(B), "steps": int(nsim),
-        "exact_lanes": int(exact.sum()), "exact_frac": float(exact.mean()),
+        "exact_lanes": int(exact.sum()), "exact_frac": float(exact.mean()), "exact_strict_frac": float(exact_s.mean()),
+        "solves_strict_prefix": int(np.minimum(upto_s, nsim).sum()), "max_du_decision_prefix": float(du_dec.max()),
         "solves_compared": int(live.sum()), "solves_exact_prefix": int(np.minimum(upto, nsim).sum()),
         "max_du_prefix": float(du.max()), "max_dx_prefix": float(dx.max()),
         "u_bar": u_bar, "du_within_bar": bool(du.max() <= u_bar),

@@ -13,7 +13,10 @@ What can and cannot be asserted (measured with tools/parity
   config 2 82 % / 63 %, config 2 quiet 99 % / 96 %, config 4 99 % / 97 %, config 5 cell 83 % / 73 %.  Engine vs oracle with
   the SAME spectral tables isolates the device arithmetic (it stays exact at the control's rate); the oracle's own tables
   add the 1e-11..1e-9 by which two `eigh` calls reconstruct M(rho)^-1.
-* Until a lane's first differing decision, controls agree far inside the task's 1e-4 bar; that is asserted exactly.
+* Controls are compared on the STRICT prefix of a lane: every decision equal and rho equal to 1e-6.  There they agree to
+  1e-6 (measured 3e-8), far inside the task's 1e-4 bar.  Past the first solve whose adapted rho differs in the 5th digit
+  the two sides run different OSQP solves -- same decisions, iterates apart by a fraction of OSQP's own 1e-3 termination
+  tolerance (measured up to 6e-4 in the controls) -- which no implementation other than OSQP's own arithmetic can avoid.
 """
 import numpy as np
 import pytest

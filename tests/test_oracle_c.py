@@ -87,7 +87,7 @@ def test_c_twin_full_horizon_against_the_batched_oracle():
     """All 300 control steps of config 2's lanes: two CPU implementations with independent linear algebra (numpy
     eigen-decomposition of M(rho) vs the twin's dense Cholesky).  The closed loop is chaotic in OSQP's discrete decisions
     (tests/test_full_horizon_parity.py), so the two agree on a FRACTION of the lanes to the end -- this is the floor any
-    float64 implementation, the CUDA engine included, is measured against -- and to the task's 1e-4 in the controls until a lane's first
+    float64 implementation, the CUDA engine included, is measured against -- and to 1e-6 in the controls until a lane's first
     differing decision."""
     from mpc_arpo_project_b200.presets import WORKLOADS, make_inputs
     from oracle.parity import as_engine_layout, full_horizon_report
@@ -101,7 +101,7 @@ def test_c_twin_full_horizon_against_the_batched_oracle():
     rep = full_horizon_report(as_engine_layout(twin), ref)
     print("C twin vs numpy oracle, config 2, 300 steps:", rep["exact_lanes"], "/", B, "max du on prefix", rep["max_du_prefix"])
     assert 0.45 <= rep["exact_frac"] < 1.0, rep           # measured 0.62 on 256 lanes; 1.0 would mean no sensitivity to show
-    assert rep["max_du_prefix"] <= 1e-4, rep             # the task's bar; measured 1.2e-5 (Cholesky vs spectral solve at rho ~ 1e4+)
+    assert rep["max_du_prefix"] <= 1e-6, rep             # while rho agrees to 1e-6 as well (oracle/parity.py); measured 1e-7
     assert rep["solves_exact_prefix"] >= 0.75 * rep["solves_compared"], rep
     assert rep["i_term_equal_frac"] >= 0.9
 
