@@ -100,6 +100,11 @@ struct PostArgs {
   uint8_t *lane_state;
   int *cnt_cur, *cnt_next;  // [4] each
   int *list_next;           // [4][B]
+  // lanes whose next solve has re-typed rows (|p^ - r|_1 < defer_below <=> some velocity-bound row's scaled bounds come within
+  // RHO_TOL, team.cuh tm_retype_operator) leave the rounds: they are listed here and carried to the end of their
+  // trajectories by the team kernel (MODE_RESUME), the one solver block that folds re-typed rows into its operator
+  double defer_below;       // <= 0: no deferral
+  int *cnt_def, *list_def;  // [4], [4][B]
   unsigned long long *solves_total;
 };
 

@@ -1184,7 +1184,7 @@ static int reset_solver_state(mpcb_handle *h) {
   CK(cudaMemsetAsync(h->zs, 0, (size_t)B * m * 8, h->stream));
   CK(cudaMemsetAsync(h->ys, 0, (size_t)B * m * 8, h->stream));
   CK(cudaMemsetAsync(h->flip, 0, (size_t)B * 4, h->stream));
-  CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->cnt, 0, 12 * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->d_tot, 0, 16 * sizeof(unsigned long long), h->stream));
   std::vector<double> r((size_t)B, std::min(std::max(h->hp.p.rho0, MPCB_RHO_MIN), MPCB_RHO_MAX));
   CK(cudaMemcpyAsync(h->rho, r.data(), (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1209,8 +1209,8 @@ extern "C" int mpcb_batch_alloc(mpcb_handle *h, int64_t B) {
     CK(cudaMalloc(&h->status, (size_t)B * 4));
     CK(cudaMalloc(&h->flip, (size_t)B * 4));
     CK(cudaMalloc(&h->lane_state, (size_t)B));
-    CK(cudaMalloc(&h->cnt, 8 * sizeof(int)));
-    CK(cudaMalloc(&h->list, (size_t)8 * B * sizeof(int)));
+    CK(cudaMalloc(&h->cnt, 12 * sizeof(int)));                       // two round buffers of 4 + the 4 deferred-lane counters
+    CK(cudaMalloc(&h->list, (size_t)12 * B * sizeof(int)));
     // LaneSim: doubles 4+6+36+4+2+2+1+2+4 = 61 per lane, ints 7 per lane
     CK(cudaMalloc(&h->lane_f64, (size_t)B * 61 * 8));
     CK(cudaMalloc(&h->lane_i32, (size_t)B * 7 * 4));
@@ -1577,7 +1577,7 @@ extern "C" int mpcb_qp_solve(mpcb_handle *h, int64_t B, const double *xhat, doub
     ta.warm = 1;
     RC(launch_team(h, ta));
   } else {
-    CK(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->cnt, 0, 12 * sizeof(int), h->stream));
     pa.cnt_cur = h->cnt + 4;
     pa.cnt_next = h->cnt;
     pa.list_next = h->list;
@@ -1775,12 +1775,26 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     pa.cnt_cur = h->cnt + 4;
     pa.cnt_next = h->cnt;
     pa.list_next = h->list;
+    const bool can_resume = mode == MODE_DISCRETE && h->team_ok && !getenv("MPCB_NO_RESUME");
+    {
+      // rounds on a block that only counts re-typed rows (wave, tile, block kernels): lanes whose solve would have them go to
+      // the team kernel instead (PostArgs::defer_below).  |p^ - r|_1 E_r < RHO_TOL for some velocity-bound row r.
+      const bool rounds_on_team = !want_tile(h) && !(want_wave(h, true) && mode == MODE_DISCRETE) && want_team(h);
+      pa.defer_below = 0.0;
+      pa.cnt_def = h->cnt + 8;
+      pa.list_def = h->list + (size_t)8 * B;
+      if (can_resume && !rounds_on_team && h->team_tm && h->thdr.r3ok && !getenv("MPCB_NO_DEFER")) {
+        const mpcb_problem &pp = h->hp.p;
+        double emax = 0.0;
+        for (int k = 0; k <= pp.Nb; ++k) emax = std::max(emax, h->hp.E[4 * (pp.Nx + 1) + 5 * k + 3]);
+        if (emax > 0.0) pa.defer_below = MPCB_RHO_TOL / emax;
+      }
+    }
     const int pgrid = (int)((B + 127) / 128);
     init_kernel<<<pgrid, 128, 0, h->stream>>>(pa, d_x0);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;
     TeamArgs tr;
-    const bool can_resume = mode == MODE_DISCRETE && h->team_ok && !getenv("MPCB_NO_RESUME");
     if (can_resume) {
       fill_team_args(h, tr, MODE_RESUME);
       tr.nsteps = nsteps;
@@ -1802,6 +1816,23 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     const bool forced_wave = getenv("MPCB_SOLVER") && strcmp(getenv("MPCB_SOLVER"), "wave") == 0;
     const bool use_wave = !want_tile(h) && want_wave(h, true) && (mode == MODE_DISCRETE || forced_wave);
     RC(run_rounds(h, aa, pa, 0, want_tile(h), use_wave, can_resume ? &tr : nullptr, below));
+    if (pa.defer_below > 0.0) {          // lanes that left the rounds because OSQP re-types their rows: team kernel, to the end
+      CK(cudaMemcpyAsync(h->h_cnt, h->cnt + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      long ndef = 0;
+      for (int v = 0; v < 4; ++v) ndef += h->h_cnt[v];
+      if (ndef > 0) {
+        TeamArgs ta = tr;
+        ta.cnt = h->cnt + 8;
+        ta.list = h->list + (size_t)8 * B;
+        CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+        const int tgrid = (int)std::min<long>(ndef, (long)h->num_sms * h->team_ctas);
+        ((team_fn)h->team_fn_ptr)<<<tgrid, h->team_threads, h->team_smem, h->stream>>>(ta);
+        CK(cudaGetLastError());
+        h->ctr.kernel_launches += 1;
+        h->ctr.admm_launches += 1;
+      }
+    }
     finalize_kernel<<<pgrid, 128, 0, h->stream>>>(pa, h->d_stats, h->flip);
     CK(cudaGetLastError());
     h->ctr.kernel_launches += 1;

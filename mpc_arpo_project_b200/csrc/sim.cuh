@@ -182,19 +182,23 @@ __device__ __forceinline__ int write_qp_params(const PostArgs &a, int ln, const 
 }
 
 // Append live lanes to the next round's per-variant lists (warp-aggregated atomics).
-__device__ __forceinline__ void bin_lane(const PostArgs &a, int ln, bool live, int variant) {
+// `fresh`: the lane starts a NEW solve (its parameters were just refreshed) -- the moment a lane may be deferred.
+__device__ __forceinline__ void bin_lane(const PostArgs &a, int ln, bool live, int variant, bool fresh = false) {
   const unsigned lane = threadIdx.x & 31u;
+  const bool defer = live && fresh && a.defer_below > 0.0 && a.par[(size_t)4 * a.B + ln] < a.defer_below;
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
-    const unsigned mask = __ballot_sync(0xffffffffu, live && variant == v);
+    const unsigned mask = __ballot_sync(0xffffffffu, live && !defer && variant == v);
     if (mask) {
       int base = 0;
       const int leader = __ffs(mask) - 1;
       if ((int)lane == leader) base = atomicAdd(&a.cnt_next[v], __popc(mask));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (live && variant == v) a.list_next[(size_t)v * a.B + base + __popc(mask & ((1u << lane) - 1u))] = ln;
+      if (live && !defer && variant == v) a.list_next[(size_t)v * a.B + base + __popc(mask & ((1u << lane) - 1u))] = ln;
     }
   }
+  if (__any_sync(0xffffffffu, defer) && defer)          // rare: plain atomics
+    a.list_def[(size_t)variant * a.B + atomicAdd(&a.cnt_def[variant], 1)] = ln;
 }
 
 // Controller selection + sequential norm clip (trajectorySimulate.py:299-319; no-debris path).
@@ -362,7 +366,7 @@ __global__ void init_kernel(const __grid_constant__ PostArgs a, const double *__
       live = true;
     }
   }
-  bin_lane(a, ln, live, variant);
+  bin_lane(a, ln, live, variant, true);
 }
 
 // QP-only seam (mpcb_qp_solve): parameters from xhat, every lane solves.
@@ -390,7 +394,7 @@ __global__ void qp_prepare_kernel(const __grid_constant__ PostArgs a, const doub
 __global__ void post_kernel(const __grid_constant__ PostArgs a) {
   const int ln = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t B = a.B;
-  bool live = false;
+  bool live = false, fresh = false;
   int variant = 0;
   if (blockIdx.x == 0 && threadIdx.x < 4) a.cnt_cur[threadIdx.x] = 0;   // consumed by the ADMM kernel before us
   if (ln < a.B) {
@@ -520,12 +524,13 @@ __global__ void post_kernel(const __grid_constant__ PostArgs a) {
         stt = LANE_SOLVING;
         a.iter[ln] = 0;
         a.status[ln] = -10;
+        fresh = true;
       }
       a.lane_state[ln] = stt;
     }
     live = (stt == LANE_SOLVING);
   }
-  bin_lane(a, ln, live, variant);
+  bin_lane(a, ln, live, variant, fresh);
 }
 
 // Final per-lane results + batch statistics (test/disturbRejComp.py:87-100, success_rates_test.py:66-75).

@@ -513,13 +513,17 @@ def test_operator_cache_does_not_change_results(monkeypatch):
     assert np.array_equal(a.x_true, b.x_true, equal_nan=True) and np.array_equal(a.ctrl_hist, b.ctrl_hist, equal_nan=True)
 
 
-@pytest.mark.parametrize("Nx,B", [(10, 48), (20, 24), (30, 16)])
-def test_row_retyping_on_the_team_kernel(Nx, B):
+@pytest.mark.parametrize("Nx,B,env", [(10, 48, {}), (20, 24, {}), (30, 16, {}),
+                                      (10, 200, {"MPCB_SOLVER": "wave", "MPCB_RESUME_BELOW": "0"})],
+                         ids=["nx10", "nx20", "nx30", "nx10_wave_rounds_defer_to_team"])
+def test_row_retyping_on_the_team_kernel(Nx, B, env, monkeypatch):
     """lanes parked next to the target make OSQP re-type the velocity-bound rows as equalities
     (rho_vec = 1e3 rho + refactor).  The team kernel folds the re-typed rows into its tensor-memory operator with one
     Sherman-Morrison step per row; iteration counts, statuses and controls must follow the oracle that models the
     re-typing (checked against the scalar KKT oracle in tests/test_batched_ref.py) -- and differ from the one that does not."""
     from test_batched_ref import retype_lanes
+    for k, v in env.items():         # last case: rounds of the multi-RHS wave kernel, which hands re-typing lanes to the team kernel
+        monkeypatch.setenv(k, v)
     case, x0, noise = retype_lanes(B=B, seed=11, Nx=Nx)
     sc, mp, fp, _ = make_params(M, case)
     got = M.trajectorySimulateBatch(sc, mp, fp, None, x0, noise)
