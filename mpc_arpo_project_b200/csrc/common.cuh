@@ -10,7 +10,7 @@
 #define MPCB_DIV_TOL 1e-30
 
 // lane_state
-enum : uint8_t { LANE_SOLVING = 0, LANE_SOLVE_DONE = 1, LANE_FINISHED = 2 };
+enum : uint8_t { LANE_SOLVING = 0, LANE_SOLVE_DONE = 1, LANE_FINISHED = 2, LANE_DEFERRED = 3 };   // DEFERRED: left the rounds, waits for the team kernel
 
 // Byte offsets of the sections of the per-variant constant blob staged into shared memory.
 struct BlobHdr {

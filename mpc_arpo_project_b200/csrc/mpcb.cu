@@ -1785,9 +1785,9 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
       pa.list_def = h->list + (size_t)8 * B;
       if (can_resume && !rounds_on_team && h->team_tm && h->thdr.r3ok && !getenv("MPCB_NO_DEFER")) {
         const mpcb_problem &pp = h->hp.p;
-        double emax = 0.0;
-        for (int k = 0; k <= pp.Nb; ++k) emax = std::max(emax, h->hp.E[4 * (pp.Nx + 1) + 5 * k + 3]);
-        if (emax > 0.0) pa.defer_below = MPCB_RHO_TOL / emax;
+        double emin = 1e300;              // the row with the smallest scale factor is re-typed first
+        for (int k = 0; k <= pp.Nb; ++k) emin = std::min(emin, h->hp.E[4 * (pp.Nx + 1) + 5 * k + 3]);
+        if (emin > 0.0 && emin < 1e300) pa.defer_below = MPCB_RHO_TOL / emin * (1.0 + 1e-12);
       }
     }
     const int pgrid = (int)((B + 127) / 128);

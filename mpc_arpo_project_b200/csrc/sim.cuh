@@ -197,8 +197,10 @@ __device__ __forceinline__ void bin_lane(const PostArgs &a, int ln, bool live, i
       if (live && !defer && variant == v) a.list_next[(size_t)v * a.B + base + __popc(mask & ((1u << lane) - 1u))] = ln;
     }
   }
-  if (__any_sync(0xffffffffu, defer) && defer)          // rare: plain atomics
+  if (__any_sync(0xffffffffu, defer) && defer) {        // rare: plain atomics
     a.list_def[(size_t)variant * a.B + atomicAdd(&a.cnt_def[variant], 1)] = ln;
+    a.lane_state[ln] = LANE_DEFERRED;                   // post_kernel re-bins LANE_SOLVING lanes every round: not this one
+  }
 }
 
 // Controller selection + sequential norm clip (trajectorySimulate.py:299-319; no-debris path).
