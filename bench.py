@@ -201,9 +201,13 @@ def cpu_arm(wl, lanes, cores, seed):
         s, w = cpu_python_run(wl, lanes, cores, seed)
         return s, w, "port", "oracle/sim_ref.py (restated per-trajectory Python + OSQP loop, RK4 plant)"
     s, w = cpu_twin_run(wl, lanes, cores, seed)
+    note = ""
+    if wl["case"].get("debris"):
+        note = ("; the twin runs the DEBRIS-FREE problem of the same horizon (it has no obstacle geometry): a lower bound on the "
+                "reference's cost per solve, which re-equilibrates and refactors at every step once a Debris object exists")
     return s, w, "port", ("oracle/c/mpc_ref.c (compiled per-trajectory loop of the reference: OSQP-equivalent ADMM with a dense "
                           "Cholesky of the reduced KKT system, UKF, one trajectory per thread; osqp / filterpy / control are not "
-                          "installable offline)")
+                          "installable offline)" + note)
 
 
 def run_reference_arm(args, wl):
@@ -264,17 +268,28 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # NCCL announces its version on STDOUT when the first communicator comes up; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device(f"cuda:{local}")
 
     B = args.lanes or wl["lanes"]
     kind = wl["kind"]
     case = wl["case"]
-    sc, mp, fp, _ = make_params(case)
+    sc, mp, fp, debris = make_params(case)
     record = ("x_true", "x_est", "ctrl", "ctrlr_seq")          # the SimRun fields of the reference
     plan = None
     if kind == "D":
-        prob = M.build_problem(sc, mp, fp, None)
+        prob = M.build_problem(sc, mp, fp, debris)
         nsteps = int(sc.T_final / sc.time_stp)
         engines = [M.Engine(prob, device=local, pin_outputs=True)]
     elif kind == "C":
@@ -431,7 +446,7 @@ def main():
             lo = e
         mix = {"status_fraction": {nm: float(((st == k) & live).sum() / tot) for k, nm in names.items()},
                "iters_per_solve_hist": hist, "max_iterations_one_lane": int((it * live).sum(axis=0).max())}
-    if rank == 0 and args.parity_lanes > 0 and kind in ("D", "S"):
+    if rank == 0 and args.parity_lanes > 0 and kind in ("D", "S") and not prob.has_debris:
         # the oracle as the CHECKER (never timed, never on the product path): a slice of the workload, all 300 steps, lane by
         # lane (oracle/parity.py; DESIGN.md section 4 explains what "exact" can and cannot mean here)
         from oracle.batched_ref import simulate_discrete_batch

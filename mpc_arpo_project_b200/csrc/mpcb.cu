@@ -1006,8 +1006,23 @@ static int launch_generic(mpcb_handle *h, GenArgs &g) {
   g.stats = h->d_stats;
   const int grid = (int)std::min<int64_t>(h->B, h->gen_grid);
   CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), h->stream));
+  if (h->timing) {
+    while (h->ev_pool.size() < 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+    CK(cudaEventRecord(h->ev_pool[0], h->stream));
+  }
   generic_lane_kernel<<<grid, GEN_THREADS, h->gen_smem, h->stream>>>(g);
   CK(cudaGetLastError());
+  if (h->timing) {
+    CK(cudaEventRecord(h->ev_pool[1], h->stream));
+    CK(cudaEventSynchronize(h->ev_pool[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev_pool[0], h->ev_pool[1]));
+    h->ctr.admm_ms += ms;
+  }
   h->ctr.kernel_launches += 1;
   h->ctr.admm_launches += 1;
   h->ctr.rounds += 1;
