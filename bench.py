@@ -498,14 +498,18 @@ def main():
         blocks = eng.solver_blocks()
         Bcell = B if plan is None else Bc
         wave_min = int(os.environ.get("MPCB_WAVE_MIN_LANES", "16384"))
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        ctas4 = (Bcell + 31) // 32                 # mpcb.cu wave_small_window: every SM (or at least 3 of 4) gets one 4-warp CTA
+        wave4 = (not os.environ.get("MPCB_NO_WAVE4")) and 4 * ctas4 >= 3 * sms and ctas4 <= sms and prob.n == 81
         if forced in ("block", "tile", "wave"):
             kern = {"block": "admm_block_kernel", "tile": "admm_tile_kernel", "wave": "admm_wave_kernel + team_kernel (resume)"}[forced]
         elif prob.has_debris:
             kern = "generic_lane_kernel"
         elif not blocks["team"]:
             kern = "admm_block_kernel"
-        elif forced != "team" and blocks["wave"] and Bcell >= wave_min and kind != "C":
-            kern = "admm_wave_kernel (multi-RHS DMMA rounds) + team_kernel (takes the last lanes over mid-flight)"
+        elif forced != "team" and blocks["wave"] and kind != "C" and (Bcell >= wave_min or wave4):
+            kern = ("admm_wave_kernel<%d warps> (multi-RHS DMMA rounds) + team_kernel (takes the last lanes over mid-flight)"
+                    % (4 if (Bcell + 31) // 32 <= sms else 8))
         else:
             kern = "team_kernel" + (" (whole closed loop, one launch per step)" if kind != "C" else " (list mode: one launch per round of solves)")
         traffic = None

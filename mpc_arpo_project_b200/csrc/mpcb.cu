@@ -131,7 +131,8 @@ struct mpcb_handle {
   WaveHdr wave_hdr;
   WaveConst wave_k;
   unsigned char *d_wave_blob[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t wave_smem = 0;
+  size_t wave_smem = 0, wave_smem4 = 0;
+  int wave_warps_now = WAVE_WARPS;  // CTA size of the current simulate call's wave rounds (8 or 4 warps)
   int64_t wave_min_lanes = 16384;      // default solver block of the round-based simulators from this batch size on
   // per-lane path (debris lanes)
   bool generic_ok = false;
@@ -845,6 +846,7 @@ static int build_wave_tables(mpcb_handle *h) {
   hd.off_M1 = take(8 * 32);
   hd.total = off;
   h->wave_smem = (size_t)hd.total + (size_t)WAVE_WARPS * 8 * (WAVE_LD + WAVE_LDV + WAVE_LD) * 8;
+  h->wave_smem4 = (size_t)hd.total + (size_t)4 * 8 * (WAVE_LD + WAVE_LDV + WAVE_LD) * 8;
   if (h->wave_smem > 227 * 1024) return MPCB_OK;
   for (int v = 0; v < 4; ++v) {
     std::vector<unsigned char> b(hd.total, 0);
@@ -884,7 +886,8 @@ static int build_wave_tables(mpcb_handle *h) {
     CK(cudaMalloc(&h->d_wave_blob[v], hd.total));
     CK(cudaMemcpy(h->d_wave_blob[v], b.data(), hd.total, cudaMemcpyHostToDevice));
   }
-  CK(cudaFuncSetAttribute((const void *)admm_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wave_smem));
+  CK(cudaFuncSetAttribute((const void *)admm_wave_kernel<WAVE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wave_smem));
+  CK(cudaFuncSetAttribute((const void *)admm_wave_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->wave_smem4));
   h->wave_hdr = hd;
   h->wave_k = K;
   h->wave_ok = true;
@@ -1322,14 +1325,23 @@ static bool want_tile(const mpcb_handle *h) {
   if (e && *e) return strcmp(e, "tile") == 0;
   return h->B >= h->tile_min_lanes;
 }
+// 4-warp wave CTAs: between 3/4 of the SMs and all of them get one CTA of 32 lanes
+static bool wave_small_window(const mpcb_handle *h) {
+  if (getenv("MPCB_NO_WAVE4")) return false;
+  const int64_t ctas = (h->B + 31) / 32;
+  return 4 * ctas >= 3 * (int64_t)h->num_sms && ctas <= h->num_sms;
+}
 static bool want_wave(const mpcb_handle *h, bool round_based) {
   if (!h->wave_ok) return false;
   const char *e = getenv("MPCB_SOLVER");
   if (e && *e) return strcmp(e, "wave") == 0;
   // Large batches: rounds of the multi-RHS wave kernel (2x the team kernel's throughput once every SM holds 64 lanes), the
-  // last lanes handed to the team kernel mid-flight.  Small batches stay on the team kernel's whole-loop launch: a round
-  // of 4096 lanes would fill 64 of 148 SMs.
-  return round_based && h->B >= h->wave_min_lanes;
+  // last lanes handed to the team kernel mid-flight.  Batches that give (nearly) every SM one 4-warp CTA of 32 lanes run the
+  // 4-warp instantiation (measured on BASELINE config 2, 4096 lanes: 106 ms per step against 115 on the team kernel alone).
+  // In between and below, the team kernel's whole-loop launch wins: rounds cost 25 iterations of wave latency each however
+  // few lanes they carry.
+  if (!round_based) return false;
+  return h->B >= h->wave_min_lanes || wave_small_window(h);
 }
 static bool want_team(const mpcb_handle *h) {
   if (!h->team_ok) return false;
@@ -1442,8 +1454,10 @@ static int run_rounds(mpcb_handle *h, AdmmArgs &aa, PostArgs &pa, int first_buf,
       wa.status = aa.status; wa.par = aa.par; wa.u0 = aa.u0; wa.lane_state = aa.lane_state; wa.flip = aa.flip;
       wa.iter_total = aa.iter_total;
       int wgrid = 0;
-      for (int v = 0; v < 4; ++v) wgrid += (h->h_cnt[v] + 8 * WAVE_WARPS - 1) / (8 * WAVE_WARPS);
-      admm_wave_kernel<<<wgrid, 32 * WAVE_WARPS, h->wave_smem, h->stream>>>(wa);
+      const int ww = h->wave_warps_now;
+      for (int v = 0; v < 4; ++v) wgrid += (h->h_cnt[v] + 8 * ww - 1) / (8 * ww);
+      if (ww == 4) admm_wave_kernel<4><<<wgrid, 32 * 4, h->wave_smem4, h->stream>>>(wa);
+      else admm_wave_kernel<WAVE_WARPS><<<wgrid, 32 * WAVE_WARPS, h->wave_smem, h->stream>>>(wa);
     } else if (use_tile) {
       TileArgs ta;
       memset(&ta, 0, sizeof ta);
@@ -1830,6 +1844,7 @@ static int simulate(mpcb_handle *h, int mode, int64_t B, int32_t nsteps, int32_t
     // rounds, which pay a post_kernel pass (500 RK4 substeps per lane) and a host round trip per 25 iterations.
     const bool forced_wave = getenv("MPCB_SOLVER") && strcmp(getenv("MPCB_SOLVER"), "wave") == 0;
     const bool use_wave = !want_tile(h) && want_wave(h, true) && (mode == MODE_DISCRETE || forced_wave);
+    h->wave_warps_now = ((B + 31) / 32 <= h->num_sms && !getenv("MPCB_NO_WAVE4")) ? 4 : WAVE_WARPS;
     RC(run_rounds(h, aa, pa, 0, want_tile(h), use_wave, can_resume ? &tr : nullptr, below));
     if (pa.defer_below > 0.0) {          // lanes that left the rounds because OSQP re-types their rows: team kernel, to the end
       CK(cudaMemcpyAsync(h->h_cnt, h->cnt + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -39,9 +39,8 @@
 #define WAVE_NT 11        // 8-wide tiles
 #define WAVE_LD 84        // stride of Vp rows and of the tile's n-vector rows: 4 (mod 16) keeps both fragment patterns conflict free
 #define WAVE_LDV 52       // stride of the dynamics-dual exchange rows (48 used)
-#ifndef WAVE_WARPS
-#define WAVE_WARPS 8
-#endif
+#define WAVE_WARPS 8      // warps (8-lane tiles) per CTA at large batches; a 4-warp instantiation serves batches that would
+                          // otherwise leave SMs without a CTA (admm_wave_kernel<4>: 78 % of the 8-warp throughput per SM)
 #define WAVE_NVS 28       // variable slots per thread: x 3x4, u 2x2, s 2x5, d 2
 #define WAVE_NRS 43       // row slots per thread: dyn 3x4, los 3x5, box-u 2x2, box-s 2x5, pin 2
 #define WAVE_INF 1e30
@@ -228,7 +227,8 @@ struct WaveRow {
   __device__ __forceinline__ double vee(int slot, double z, double y) const { return fma(ka[4 * slot], rho, kb[4 * slot]) * z - y; }
 };
 
-__global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __grid_constant__ WaveArgs a) {
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) admm_wave_kernel(const __grid_constant__ WaveArgs a) {
   constexpr int NX = WAVE_NX, NC = WAVE_NC, NB = WAVE_NB, N = WAVE_N, M = WAVE_M, KS = WAVE_KS, NT = WAVE_NT, LD = WAVE_LD,
                 LDV = WAVE_LDV;
   constexpr int nX = 4 * (NX + 1), RB = nX + 5 * (NX + 1);       // first input/slack variable; first box row
@@ -237,16 +237,16 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
   const WaveConst &K = a.k;
   const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31, g = lid >> 2, c = lid & 3;
 
-  // ---- which (variant, group of 8 * WAVE_WARPS lanes) is this CTA
+  // ---- which (variant, group of 8 * WARPS lanes) is this CTA
   int b = blockIdx.x, v = 0, cnt_v = 0;
   for (; v < 4; ++v) {
     cnt_v = a.cnt[v];
-    const int nt = (cnt_v + 8 * WAVE_WARPS - 1) / (8 * WAVE_WARPS);
+    const int nt = (cnt_v + 8 * WARPS - 1) / (8 * WARPS);
     if (b < nt) break;
     b -= nt;
   }
   if (v == 4) return;
-  for (int o = threadIdx.x * 16; o < h.total; o += 32 * WAVE_WARPS * 16)
+  for (int o = threadIdx.x * 16; o < h.total; o += 32 * WARPS * 16)
     *reinterpret_cast<int4 *>(smem + o) = *reinterpret_cast<const int4 *>(a.blob[v] + o);
   __shared__ uint32_t s_tmem;
   if (warp == 0) {
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32 * WAVE_WARPS, 1) admm_wave_kernel(const __g
   double *vb = wbase + 8 * LD + g * LDV;
   double *dscb = wbase + 8 * (LD + LDV) + g * LD;
 
-  const int pos = (b * WAVE_WARPS + warp) * 8 + g;
+  const int pos = (b * WARPS + warp) * 8 + g;
   const bool valid = pos < cnt_v;
   const bool tile_live = __ballot_sync(0xffffffffu, valid) != 0;
   const int ln = valid ? a.list[(size_t)v * a.B + pos] : 0;

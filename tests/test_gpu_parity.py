@@ -38,10 +38,10 @@ def test_qp_solve_cold_and_warm(Nx):
     _qp_seam(Nx, 48)
 
 
-@pytest.mark.parametrize("solver,B", [("tile", 48), ("tile", 77), ("block", 48), ("team", 48)])
+@pytest.mark.parametrize("solver,B", [("tile", 48), ("tile", 77), ("block", 48), ("team", 48), ("wave", 48), ("wave", 77)])
 def test_qp_solve_every_solver_block(solver, B, monkeypatch):
-    """The same seam with each of the three solver blocks forced (MPCB_SOLVER): the DMMA tile kernel
-    (8 lanes per warp; B = 77 leaves ragged tiles in every sign variant), the warp-per-lane block
+    """The same seam with each of the solver blocks forced (MPCB_SOLVER): the multi-RHS wave kernel and the older DMMA tile
+    kernel (8 lanes per warp; B = 77 leaves ragged tiles in every sign variant), the warp-per-lane block
     kernel and the persistent team kernel all reproduce the oracle's iterates."""
     monkeypatch.setenv("MPCB_SOLVER", solver)
     _qp_seam(10, B)
@@ -172,9 +172,10 @@ def test_discrete_closed_loop_matches_batched_oracle(name):
     _closed_loop(name)
 
 
-@pytest.mark.parametrize("solver", ["tile", "block"])
+@pytest.mark.parametrize("solver", ["tile", "block", "wave"])
 def test_discrete_closed_loop_every_solver_block(solver, monkeypatch):
     monkeypatch.setenv("MPCB_SOLVER", solver)
+    monkeypatch.setenv("MPCB_RESUME_BELOW", "0")      # wave: stay on the rounds to the end instead of handing the lanes to the team kernel
     for name, (case, _) in DISCRETE.items():
         if case.get('Nx', 10) == 10:
             _closed_loop(name)

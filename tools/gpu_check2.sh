@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-BENCH_VERBOSE=1 timeout 1500 python bench.py --workload config1 --steps 2 --warmup 3 > gpurun_out/r2_bench_config1.json 2> gpurun_out/r2_bench_config1.err; tail -7 gpurun_out/r2_bench_config1.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench_config1.json'));print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['roofline']['kernel'], d['cpu_baseline']['value'])"
-BENCH_VERBOSE=1 MPCB_SOLVER=block timeout 900 python bench.py --workload config1 --steps 2 --warmup 3 --no-cpu-baseline --parity-lanes 0 2>&1 | grep "\[bench\] step" | tail -3
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_full_horizon_parity.py -q -s -k "every_solver_block or wave" 2>&1 | grep -v "^$" | tail -14
