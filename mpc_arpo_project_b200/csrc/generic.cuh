@@ -413,10 +413,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
             const double piv = 1.0 / buf[k];
             const double g = row_get(k) * piv;                   // S_ik / S_kk
             const bool is_k = tid == k, is_next = tid == k + 1;
-            const double mul = is_k ? piv : -g, diag = is_k ? piv : -g;
-            auto upd = [&](int j, double b, double old) -> double {        // one FMA per entry for owner and non-owner alike
-              return (j == k) ? diag : fma(mul, b, is_k ? 0.0 : old);
-            };
+            const double mul = is_k ? piv : -g, diag = is_k ? piv : -g, keep = is_k ? 0.0 : 1.0;
+            // One DMUL + one DFMA per entry for owner and non-owner alike; only the group that holds the pivot column pays
+            // the compare / select (ncu: FSEL + ISETP used to dominate this loop, 68 % of the kernel's samples).
+            auto updf = [&](double b, double old) -> double { return fma(mul, b, keep * old); };
+            auto upds = [&](int j, double b, double old) -> double { return (j == k) ? diag : fma(mul, b, keep * old); };
             const double2 *buf2 = reinterpret_cast<const double2 *>(buf);
             double2 *nxt2 = reinterpret_cast<double2 *>(nxt);
             int j0 = 0;
@@ -433,13 +434,26 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
               tmem_wait_ld2(q[0], q[1]);
               tmem_wait_ld2(q[2], q[3]);
               double2 r2[16];
+              if ((unsigned)(k - j0) < 32u) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int gq = i >> 2, e = (i & 3) * 4;        // entries 2i, 2i+1 of the group = registers e..e+3 of load gq
+                  r2[i].x = upds(j0 + 2 * i, b2[i].x, u2d(q[gq][e], q[gq][e + 1]));
+                  r2[i].y = upds(j0 + 2 * i + 1, b2[i].y, u2d(q[gq][e + 2], q[gq][e + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int gq = i >> 2, e = (i & 3) * 4;
+                  r2[i].x = updf(b2[i].x, u2d(q[gq][e], q[gq][e + 1]));
+                  r2[i].y = updf(b2[i].y, u2d(q[gq][e + 2], q[gq][e + 3]));
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int g = i >> 2, e = (i & 3) * 4;           // entries 2i, 2i+1 of the group = registers e..e+3 of load g
-                r2[i].x = upd(j0 + 2 * i, b2[i].x, u2d(q[g][e], q[g][e + 1]));
-                r2[i].y = upd(j0 + 2 * i + 1, b2[i].y, u2d(q[g][e + 2], q[g][e + 3]));
-                q[g][e] = (uint32_t)__double2loint(r2[i].x); q[g][e + 1] = (uint32_t)__double2hiint(r2[i].x);
-                q[g][e + 2] = (uint32_t)__double2loint(r2[i].y); q[g][e + 3] = (uint32_t)__double2hiint(r2[i].y);
+                const int gq = i >> 2, e = (i & 3) * 4;
+                q[gq][e] = (uint32_t)__double2loint(r2[i].x); q[gq][e + 1] = (uint32_t)__double2hiint(r2[i].x);
+                q[gq][e + 2] = (uint32_t)__double2loint(r2[i].y); q[gq][e + 3] = (uint32_t)__double2hiint(r2[i].y);
               }
               tmem_st16(taddr + 2 * j0, q[0]);
               tmem_st16(taddr + 2 * j0 + 16, q[1]);
@@ -456,10 +470,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
               const double2 ba = buf2[j0 / 2], bb = buf2[j0 / 2 + 1];
               tmem_wait_ld8(c8);
               double2 ra, rb2;
-              ra.x = upd(j0, ba.x, u2d(c8[0], c8[1]));
-              ra.y = upd(j0 + 1, ba.y, u2d(c8[2], c8[3]));
-              rb2.x = upd(j0 + 2, bb.x, u2d(c8[4], c8[5]));
-              rb2.y = upd(j0 + 3, bb.y, u2d(c8[6], c8[7]));
+              ra.x = upds(j0, ba.x, u2d(c8[0], c8[1]));
+              ra.y = upds(j0 + 1, ba.y, u2d(c8[2], c8[3]));
+              rb2.x = upds(j0 + 2, bb.x, u2d(c8[4], c8[5]));
+              rb2.y = upds(j0 + 3, bb.y, u2d(c8[6], c8[7]));
               c8[0] = (uint32_t)__double2loint(ra.x); c8[1] = (uint32_t)__double2hiint(ra.x);
               c8[2] = (uint32_t)__double2loint(ra.y); c8[3] = (uint32_t)__double2hiint(ra.y);
               c8[4] = (uint32_t)__double2loint(rb2.x); c8[5] = (uint32_t)__double2hiint(rb2.x);
@@ -473,10 +487,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_lane_kernel(const __gr
                 const double2 ba = buf2[j0 / 2], bb = buf2[j0 / 2 + 1];
                 const double o0 = sx[0], o1 = sx[TS], o2 = sx[2 * TS], o3 = sx[3 * TS];
                 double2 ra, rb2;
-                ra.x = upd(j0, ba.x, o0);
-                ra.y = upd(j0 + 1, ba.y, o1);
-                rb2.x = upd(j0 + 2, bb.x, o2);
-                rb2.y = upd(j0 + 3, bb.y, o3);
+                if ((unsigned)(k - j0) < 4u) {
+                  ra.x = upds(j0, ba.x, o0);
+                  ra.y = upds(j0 + 1, ba.y, o1);
+                  rb2.x = upds(j0 + 2, bb.x, o2);
+                  rb2.y = upds(j0 + 3, bb.y, o3);
+                } else {
+                  ra.x = updf(ba.x, o0);
+                  ra.y = updf(ba.y, o1);
+                  rb2.x = updf(bb.x, o2);
+                  rb2.y = updf(bb.y, o3);
+                }
                 sx[0] = ra.x; sx[TS] = ra.y; sx[2 * TS] = rb2.x; sx[3 * TS] = rb2.y;
                 if (is_next) { nxt2[j0 / 2] = ra; nxt2[j0 / 2 + 1] = rb2; }
               }

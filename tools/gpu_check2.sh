@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_full_horizon_parity.py -q -s -k "every_solver_block or wave" 2>&1 | grep -v "^$" | tail -14
+for rb in 2500 2960 3300 3600; do echo -n "rb=$rb: "; MPCB_RESUME_BELOW=$rb BENCH_VERBOSE=1 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --parity-lanes 0 2>&1 | grep "\[bench\] step" | head -6 | awk '{s+=$6; printf "%s ", $6} END {print " avg", s/NR}'; done
