@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT
-for rb in 2500 2960 3300 3600; do echo -n "rb=$rb: "; MPCB_RESUME_BELOW=$rb BENCH_VERBOSE=1 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --parity-lanes 0 2>&1 | grep "\[bench\] step" | head -6 | awk '{s+=$6; printf "%s ", $6} END {print " avg", s/NR}'; done
+timeout 1200 python -m pytest tests/test_gpu_parity.py -q -x -k "debris or drop_in or reproducible" 2>&1 | tail -3
+BENCH_VERBOSE=1 timeout 1500 python bench.py --workload config1 --steps 2 --warmup 3 > gpurun_out/r2_bench_config1.json 2> gpurun_out/r2_bench_config1.err; tail -3 gpurun_out/r2_bench_config1.err; python -c "import json;d=json.load(open('gpurun_out/r2_bench_config1.json'));print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['roofline'], d['cpu_baseline']['value'])"
