@@ -572,3 +572,26 @@ def test_monte_carlo_reductions_match_per_lane_results():
     sc.isReject = True
     sr = M.success_rate(sc, mp, fp, None, mc_num=16, seed=1)
     assert sr["runs"] == 16 and 0 <= sr["success_count"] <= 16
+
+
+def test_batch_pipeline_equals_single_engine():
+    """pipeline.BatchPipeline keeps several engines (handles, streams) of one problem family in flight, each driven by its own
+    host thread.  Lanes are independent and every engine is deterministic: results must equal a single engine's, batch by batch."""
+    from mpc_arpo_project_b200.pipeline import BatchPipeline
+    case = dict(Nx=10, sigma=0.75, noise_length=10, T_final=15)
+    sc, mp, fp, _ = make_params(M, case)
+    prob = M.build_problem(sc, mp, fp, None)
+    nsim = 30
+    batches = []
+    for k in range(5):
+        x0, rng = lanes(case, 300 + 10 * k, 100 + k)
+        noise = 0.75 * rng.standard_normal((nsim // 10 + 1, 2, x0.shape[0]))
+        batches.append((np.ascontiguousarray(x0.T), noise))
+    with M.Engine(prob) as eng:
+        ref = [eng.simulate_discrete(x0, nz, nsim, ("x_true", "ctrl", "iters")) for x0, nz in batches]
+    with BatchPipeline(prob, depth=3) as pipe:
+        got = pipe.map_discrete(batches, nsim, ("x_true", "ctrl", "iters"))
+    for a, b in zip(got, ref):
+        assert a.stats["qp_solves"] == b.stats["qp_solves"] and a.stats["sum_final_dist"] == b.stats["sum_final_dist"]
+        np.testing.assert_array_equal(a.iters, b.iters)
+        assert np.array_equal(a.x_true, b.x_true, equal_nan=True) and np.array_equal(a.ctrl_hist, b.ctrl_hist, equal_nan=True)
