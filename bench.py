@@ -564,6 +564,11 @@ def main():
             if kind != "C":
                 s1, w1 = cpu_twin_run(wl, max(2 if kind == "D" else 20, lanes // (3 * cores)), 1, SEED0)
                 cb["one_core"] = s1 / w1
+            if kind == "D" and not prob.has_debris and prob.Nx <= 20:
+                # the restated PYTHON path (numpy + restated OSQP / UKF, structured like the reference's loop),
+                # one trajectory per core -- what the reference's interpreter-bound loop costs, beside the compiled twin
+                s2, w2 = cpu_python_run(wl, cores, cores, SEED0)
+                cb["python_restatement"] = {"value": s2 / w2, "cores": cores, "sample": f"{cores} lanes, full horizon, {w2:.1f} s wall"}
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     for e in engines:
