@@ -554,10 +554,10 @@ def main():
             cores = os.cpu_count() or 1
             if kind == "C":
                 lanes = 2 * cores
-            else:       # a pilot sizes the sample to ~12 s of wall time on all cores (the families differ 40x in cost per solve)
+            else:       # a pilot sizes the sample to 10-20 s of wall time on all cores (the families differ 40x in cost per solve)
                 pilot = (2 if kind == "D" else 1) * cores * (20 if kind == "S" else 1)
                 s0, w0 = cpu_twin_run(wl, pilot, cores, SEED0 - 7)
-                lanes = int(min(65536, max(pilot, pilot * 12.0 / max(w0, 1e-3))))
+                lanes = int(min(65536, max(pilot, pilot * 24.0 / max(w0, 1e-3))))
             s, w, ckind, desc = cpu_arm(wl, lanes, cores, SEED0)
             cb = {"value": s / w, "unit": UNIT, "cores": cores, "kind": ckind,
                   "sample": f"{lanes} lanes of {args.workload}, full horizon, {w:.1f} s wall: {desc}"}
