@@ -405,9 +405,11 @@ def main():
     c1 = [e.counters() for e in engines]
 
     # end-to-end leg: same steps through the public API with pinned HOST buffers (H2D + D2H inside)
+    # (the SAME lanes as the device-resident leg, step by step: per-seed step times spread 104-194 ms on config 2, so two legs on
+    # different seeds would not be comparable)
     step(n_dev, False)
     sync_all()
-    ms_e2e, solves_e2e, res_h = timed(n_dev + 1, args.steps, False)
+    ms_e2e, solves_e2e, res_h = timed(args.warmup, args.steps, False)
     sync_all()
     if plan is None:
         d2h = sum(getattr(res_h, k).nbytes for k in ("x_true", "x_est", "ctrl_hist", "ctrlr_seq", "i_term", "isSuccess",
