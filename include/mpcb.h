@@ -128,7 +128,8 @@ typedef struct mpcb_counters {
   int64_t kernel_launches;  /* kernels launched by this library */
   int64_t admm_launches;    /* of which: ADMM block kernel */
   int64_t rounds;           /* lockstep rounds (one 25-iteration block per live lane) */
-  int64_t flip_lanes;       /* lanes that hit the unsupported "E*val < RHO_TOL" row reclassification */
+  int64_t flip_lanes;       /* lanes in which OSQP re-types a velocity-bound row as an equality (scaled u - l < 1e-4): modelled by the
+                               team / wave+team / per-lane kernels, only counted by the block (Nx = 40) and tile kernels */
   int64_t operator_rebuilds;/* per-trajectory KKT operator rebuilds (rho adapted or velocity signs flipped) */
   double admm_ms;           /* CUDA-event time spent in the ADMM block kernel (if timing enabled) */
   double total_ms;          /* CUDA-event time of the whole call, on the handle's stream */
