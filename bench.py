@@ -516,7 +516,12 @@ def main():
             kern = "team_kernel" + (" (whole closed loop, one launch per step)" if kind != "C" else " (list mode: one launch per round of solves)")
         traffic = None
         try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (null if never captured)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kern.split(' ')[0]}:{args.workload}")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{kern.split(' ')[0]}:{args.workload}")
+            w4, ho = tj.get(f"admm_wave_kernel<4>:{args.workload}"), tj.get(f"team_kernel_handover:{args.workload}")
+            if kern.startswith("admm_wave_kernel<4") and w4 and ho and admm_launches > 1:
+                # rounds + one hand-over launch: launch-weighted mean of the two kernels' captured bytes
+                traffic = int((w4 * (admm_launches - 1) + ho) / admm_launches)
         except Exception:
             pass
         tot_stats = np.asarray(res["stats"]).reshape(-1, _lib.NSTATS).sum(axis=0) if plan is not None else res.stats_vec
